@@ -1,0 +1,163 @@
+/*
+ * libgoat_sm100 -- C ABI of the B200 (sm_100a) kernels behind the GOAT cross-modal hot path.
+ *
+ * The reference (CrystalSixone/VLN-GOAT) has no FFI / plugin layer for this path: every op is a
+ * stock torch call inside Python nn.Modules.  The drop-in boundary is
+ * therefore the Python module API (vln_goat_b200.modules mirrors the reference class names and
+ * state_dict keys) and THIS header is the operator interface those modules bind through ctypes.
+ * Each entry point cites the reference code it replaces.  P/ = pretrain_src/, M/ = map_nav_src/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise.
+ *  - the caller owns every buffer (inputs, outputs, workspaces); the library allocates nothing
+ *    and keeps no pointer after return.  Workspace sizes come from goat_*_workspace_bytes().
+ *  - all work is enqueued on the stream passed in; no implicit synchronisation, no default
+ *    stream, safe under CUDA-graph capture.
+ *  - every function returns 0 on success, a goat_status_t otherwise; goat_last_error() returns
+ *    a thread-local human-readable message.  Nothing throws or exits.
+ *  - 16-byte alignment is required for tensor base pointers (checked, never copied).
+ *  - dtypes: GOAT_F32 runs fp32 SIMT kernels (parity mode, 1e-5); GOAT_F16 / GOAT_BF16 run the
+ *    tcgen05 tensor-core kernels with fp32 accumulation (1e-3 mode).
+ */
+#ifndef GOAT_SM100_H_
+#define GOAT_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* goat_stream_t; /* cudaStream_t */
+
+typedef enum { GOAT_OK = 0, GOAT_ERR_INVALID = 1, GOAT_ERR_CUDA = 2, GOAT_ERR_UNSUPPORTED = 3 } goat_status_t;
+typedef enum { GOAT_F32 = 0, GOAT_F16 = 1, GOAT_BF16 = 2 } goat_dtype_t;
+
+/* epilogue activation of goat_gemm */
+typedef enum {
+  GOAT_ACT_NONE = 0,
+  GOAT_ACT_GELU = 1,  /* erf-GELU, P/model/Bert_backbone.py:41-47; writes the pre-activation to aux_out */
+  GOAT_ACT_RELU = 2,  /* ClsPrediction, P/model/pretrain_goat.py:27-38 */
+  GOAT_ACT_DGELU = 3, /* multiply by gelu'(aux_in)  (backward of GELU) */
+  GOAT_ACT_DRELU = 4, /* multiply by [aux_in > 0]   (backward of ReLU; aux_in = ReLU output) */
+  GOAT_ACT_TANH = 5   /* BertPooler, P/model/Bert_backbone.py:783-795 */
+} goat_act_t;
+
+int goat_version(void);
+const char* goat_last_error(void);
+/* 1 if the tcgen05 path is usable on the current device (compute capability 10.x) */
+int goat_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------
+ * goat_gemm: out[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )
+ *
+ * Replaces every nn.Linear on the path (Q/K/V/out projections P/model/Bert_backbone.py:170-172,
+ * :302; FFN :348,:362; heads) in forward (A = activations, B = weight [N,K]) and, with the
+ * major-ness flags, both backward products (dX = dY W: b_mn_major=1; dW = dY^T X: both =1).
+ *   a_mn_major = 0: A[m,k] = A[m*lda + k]   (K contiguous)     1: A[m,k] = A[k*lda + m]
+ *   b_mn_major = 0: B[n,k] = B[n*ldb + k]   (K contiguous)     1: B[n,k] = B[k*ldb + n]
+ * epilogue, in this order: v = alpha*acc + bias[n]; activation (see goat_act_t); dropout(p, seed)
+ * with 1/(1-p) scaling; + res[m,n]; store as out_dtype into out (and a second copy in `dtype`
+ * into out2 when given).
+ * dtype F16/BF16 -> tcgen05.mma (TMA-fed, TMEM accumulators) when K, lda, ldb are multiples of 8
+ * and K >= 16; otherwise, and always for F32, the SIMT kernel.  force_simt=1 selects the SIMT
+ * kernel (used by tests as an on-device cross-check).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct goat_gemm_args {
+  int M, N, K;
+  int dtype;      /* operand dtype of A, B, aux_in, aux_out, out2 */
+  int a_mn_major, b_mn_major;
+  int lda, ldb;
+  const void* A;
+  const void* B;
+  const float* bias; /* [N] or NULL */
+  const float* res;  /* [M, ldres] fp32 or NULL */
+  int ldres;
+  const void* aux_in; /* [M, ldaux] or NULL */
+  void* aux_out;      /* [M, ldaux] or NULL */
+  int ldaux;
+  void* out;
+  int ldc;
+  int out_dtype; /* GOAT_F32 or == dtype */
+  void* out2;    /* optional, dtype `dtype` */
+  int ldc2;
+  int act;
+  float alpha;
+  float drop_p;
+  uint64_t drop_seed;
+  int force_simt;
+} goat_gemm_args;
+int goat_gemm(const goat_gemm_args* args, goat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention core: O = softmax(scale * Q K^T + kmask[b,k] + bias[b,q,k]) V   per (batch, head)
+ *
+ * Replaces P/model/Bert_backbone.py:247-290 (BertSelfAttention / RobertaSelfAttention) and the
+ * core of nn.MultiheadAttention in the pano encoder (P/model/transformer.py:174-177).
+ * Q/K/V/O are token-major: element (b, t, h, d) at base[b*sb + t*ld + h*D + d], so a fused
+ * [tokens, 3*hidden] projection output is consumed in place and O lands already head-merged
+ * (no permute/contiguous, :288-290).  kmask is the additive key mask (0 / -10000 of
+ * P/model/ops.py:25-34, or -inf for the pano encoder's key_padding_mask); bias is the additive
+ * [B,Nq,Nk] term (graph_sprels, :690-691).  lse[b,h,q] (log-sum-exp of the scaled scores) is
+ * saved for backward.  drop_p/seed: attention-probability dropout (:280).
+ * D must be 64.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct goat_attn_args {
+  int B, heads, Nq, Nk, D;
+  int dtype;
+  const void* Q;
+  const void* K;
+  const void* V;
+  int ldq, ldk, ldv;
+  long long sbq, sbk, sbv;
+  const float* kmask; /* [B, Nk] or NULL */
+  const float* bias;  /* [B, Nq, Nk] or NULL */
+  float scale;
+  void* O;
+  int ldo;
+  long long sbo;
+  float* lse; /* [B, heads, Nq] */
+  float drop_p;
+  uint64_t drop_seed;
+  /* backward only */
+  const void* dO; /* same layout as O */
+  void* dQ;       /* same layout as Q (ldq, sbq) */
+  void* dK;       /* same layout as K */
+  void* dV;       /* same layout as V */
+  float* dbias;   /* [B, Nq, Nk] fp32, ACCUMULATED into (caller zeroes), or NULL */
+} goat_attn_args;
+int goat_attn_core_fwd(const goat_attn_args* args, goat_stream_t stream);
+int goat_attn_core_bwd(const goat_attn_args* args, goat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (biased variance), fp32 statistics.
+ * Replaces nn.LayerNorm / BertLayerNorm (P/model/Bert_backbone.py:303,309,363,369,805; eps is
+ * per call site: 1e-12 or 1e-5, SURVEY.md 8a note 5).  The residual add that precedes it in the
+ * reference (:309) is fused into the producing goat_gemm epilogue (res).
+ * fwd: x [M,H] (x_dtype) -> y32 (fp32, optional) and/or y16 (y16_dtype, optional); mean/rstd [M].
+ * bwd: dy [M,H] fp32 (+ optional dy2 fp32 added to it) -> dx32 = LN'(dy) (+ dres if given),
+ *      dx16 (optional 16-bit copy of the LN' term only, masked by dropout(drop_p, seed) for the
+ *      GEMM that produced x), dgamma/dbeta [H] (written, not accumulated), dcolsum [H] optional =
+ *      column sum of the dx16 values (the bias gradient of the producing Linear).
+ *      workspace: goat_layernorm_bwd_workspace_bytes(M, H).
+ * ------------------------------------------------------------------------------------------ */
+int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, float* y32,
+                       void* y16, int y16_dtype, float* mean, float* rstd, int M, int H, goat_stream_t stream);
+size_t goat_layernorm_bwd_workspace_bytes(int M, int H);
+int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
+                       const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype, float drop_p,
+                       uint64_t drop_seed, float* dgamma, float* dbeta, float* dcolsum, void* workspace, int M, int H,
+                       goat_stream_t stream);
+
+/* column sum: out[n] = sum_m x[m*ld + n]  (bias gradients).  workspace: goat_colsum_workspace_bytes(M,N) */
+size_t goat_colsum_workspace_bytes(int M, int N);
+int goat_colsum(const void* x, int dtype, int M, int N, int ld, float* out, void* workspace, goat_stream_t stream);
+
+/* dtype conversion of n contiguous elements (fp32 master weights -> 16-bit operands, activations in/out) */
+int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, goat_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOAT_SM100_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libgoat_sm100.so (the C ABI declared in include/goat_sm100.h).
+
+The product path has no fallback: if the shared library is missing or a call fails this module
+raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``vln_goat_b200/csrc/build.sh``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgoat_sm100.so")
+
+F32, F16, BF16 = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_DGELU, ACT_DRELU, ACT_TANH = 0, 1, 2, 3, 4, 5
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("dtype", C.c_int),
+        ("a_mn_major", C.c_int), ("b_mn_major", C.c_int),
+        ("lda", C.c_int), ("ldb", C.c_int),
+        ("A", C.c_void_p), ("B", C.c_void_p),
+        ("bias", C.c_void_p), ("res", C.c_void_p), ("ldres", C.c_int),
+        ("aux_in", C.c_void_p), ("aux_out", C.c_void_p), ("ldaux", C.c_int),
+        ("out", C.c_void_p), ("ldc", C.c_int), ("out_dtype", C.c_int),
+        ("out2", C.c_void_p), ("ldc2", C.c_int),
+        ("act", C.c_int), ("alpha", C.c_float), ("drop_p", C.c_float),
+        ("drop_seed", C.c_uint64),
+        ("force_simt", C.c_int),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("heads", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("D", C.c_int),
+        ("dtype", C.c_int),
+        ("Q", C.c_void_p), ("K", C.c_void_p), ("V", C.c_void_p),
+        ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int),
+        ("sbq", C.c_longlong), ("sbk", C.c_longlong), ("sbv", C.c_longlong),
+        ("kmask", C.c_void_p), ("bias", C.c_void_p),
+        ("scale", C.c_float),
+        ("O", C.c_void_p), ("ldo", C.c_int), ("sbo", C.c_longlong),
+        ("lse", C.c_void_p),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint64),
+        ("dO", C.c_void_p), ("dQ", C.c_void_p), ("dK", C.c_void_p), ("dV", C.c_void_p),
+        ("dbias", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/goat_sm100.h declares
+SYMBOLS = {
+    "goat_version": (C.c_int, []),
+    "goat_last_error": (C.c_char_p, []),
+    "goat_device_supported": (C.c_int, []),
+    "goat_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "goat_attn_core_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "goat_attn_core_bwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "goat_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "goat_layernorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "goat_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "goat_colsum_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "goat_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "goat_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL with argtypes set.  Raises if the library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libgoat_sm100.so not found at %s -- build it first (__graft_entry__.build() or "
+                "vln_goat_b200/csrc/build.sh); there is no CPU / PyTorch fallback for this path" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().goat_last_error()
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else ""))

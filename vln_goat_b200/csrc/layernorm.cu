@@ -1,0 +1,313 @@
+// LayerNorm forward / backward (fp32 statistics), column sums and dtype casts.
+// Memory-bound helpers: one warp per row, 16-byte vector accesses, two-stage deterministic column reductions.
+#include "common.cuh"
+
+namespace goat {
+
+namespace {
+
+constexpr int LN_ROWS_PER_CTA = 4;   // 4 warps, one row each per iteration
+constexpr int LN_MAX_PER_LANE = 32;  // H <= 1024
+
+template <typename T>
+__device__ __forceinline__ float ldx(const void* p, size_t i) { return to_f<T>(reinterpret_cast<const T*>(p)[i]); }
+
+// ---------------------------------------------------------------------------------------------
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(128)
+ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+              float* __restrict__ y32, void* __restrict__ y16, float* __restrict__ mean, float* __restrict__ rstd, int M,
+              int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_ROWS_PER_CTA + warp;
+  if (row >= M) return;
+  float v[LN_MAX_PER_LANE];
+  const int n = (H + 31) / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < n) {
+      const int c = i * 32 + lane;
+      v[i] = c < H ? ldx<TX>(x, (size_t)row * H + c) : 0.f;
+      s += v[i];
+    }
+  }
+  const float mu = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < n) {
+      const int c = i * 32 + lane;
+      const float d = c < H ? v[i] - mu : 0.f;
+      q += d * d;
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / H + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < n) {
+      const int c = i * 32 + lane;
+      if (c < H) {
+        const float y = (v[i] - mu) * rs * gamma[c] + beta[c];
+        if (y32) y32[(size_t)row * H + c] = y;
+        if (y16) reinterpret_cast<TY*>(y16)[(size_t)row * H + c] = from_f<TY>(y);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: per row   xhat = (x-mu)*rstd, g = dy*gamma,
+//   dx = rstd * (g - mean(g) - xhat * mean(g*xhat))
+// column partials (dgamma = sum dy*xhat, dbeta = sum dy, dcolsum = sum dx16) per CTA into workspace
+// [gridDim.x][3][H]; a second kernel reduces them in a fixed order (deterministic).
+template <typename TX, typename TD>
+__global__ void __launch_bounds__(128)
+ln_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+              float* __restrict__ dx32, void* __restrict__ dx16, float drop_p, unsigned long long drop_seed,
+              float* __restrict__ partial, int M, int H, int rows_per_cta) {
+  extern __shared__ float sacc[];  // [4 warps][3][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (H + 31) / 32;
+  float ag[LN_MAX_PER_LANE], ab[LN_MAX_PER_LANE], ac[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) { ag[i] = 0.f; ab[i] = 0.f; ac[i] = 0.f; }
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  const float keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int row = r0 + warp; row < r1; row += 4) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      if (i < n) {
+        const int c = i * 32 + lane;
+        if (c < H) {
+          const float d = dy[(size_t)row * H + c];
+          xh[i] = (ldx<TX>(x, (size_t)row * H + c) - mu) * rs;
+          g[i] = d * gamma[c];
+          ag[i] += d * xh[i];
+          ab[i] += d;
+          s1 += g[i];
+          s2 += g[i] * xh[i];
+        } else { xh[i] = 0.f; g[i] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      if (i < n) {
+        const int c = i * 32 + lane;
+        if (c < H) {
+          const float d = rs * (g[i] - s1 - xh[i] * s2);
+          if (dx32) dx32[(size_t)row * H + c] = d + (dres ? dres[(size_t)row * H + c] : 0.f);
+          float dm = d;
+          if (drop_p > 0.f)
+            dm = rand_uniform(drop_seed, (unsigned long long)row * (unsigned long long)H + c) >= drop_p ? d * keep : 0.f;
+          if (dx16) {
+            const TD q = from_f<TD>(dm);
+            reinterpret_cast<TD*>(dx16)[(size_t)row * H + c] = q;
+            dm = to_f<TD>(q);
+          }
+          ac[i] += dm;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < n) {
+      const int c = i * 32 + lane;
+      if (c < H) {
+        sacc[(warp * 3 + 0) * H + c] = ag[i];
+        sacc[(warp * 3 + 1) * H + c] = ab[i];
+        sacc[(warp * 3 + 2) * H + c] = ac[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) {
+    const int k = e / H, c = e % H;
+    partial[((size_t)blockIdx.x * 3 + k) * H + c] =
+        sacc[(0 * 3 + k) * H + c] + sacc[(1 * 3 + k) * H + c] + sacc[(2 * 3 + k) * H + c] + sacc[(3 * 3 + k) * H + c];
+  }
+}
+
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int nparts, int H, float* dgamma, float* dbeta,
+                                       float* dcolsum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float a = 0.f, b = 0.f, d = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    a += partial[((size_t)p * 3 + 0) * H + c];
+    b += partial[((size_t)p * 3 + 1) * H + c];
+    d += partial[((size_t)p * 3 + 2) * H + c];
+  }
+  if (dgamma) dgamma[c] = a;
+  if (dbeta) dbeta[c] = b;
+  if (dcolsum) dcolsum[c] = d;
+}
+
+inline int ln_bwd_parts(int M) {
+  int parts = (M + 31) / 32;   // >= 32 rows per CTA
+  if (parts > 592) parts = 592;  // 4 CTAs per SM on 148 SMs
+  if (parts < 1) parts = 1;
+  return parts;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums: partial[rowchunk][N] then fixed-order reduce
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const void* __restrict__ x, int M, int N, int ld, int rows_per_cta, float* __restrict__ partial) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += ldx<T>(x, (size_t)r * ld + c);
+  partial[(size_t)blockIdx.y * N + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nparts, int N, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * N + c];
+  out[c] = s;
+}
+inline int colsum_parts(int M) {
+  int parts = (M + 63) / 64;
+  if (parts > 128) parts = 128;
+  if (parts < 1) parts = 1;
+  return parts;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename S, typename Dt>
+__global__ void cast_kernel(const S* __restrict__ src, Dt* __restrict__ dst, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[i + j] = from_f<Dt>(to_f<S>(src[i + j]));
+  } else {
+    for (; i < n; ++i) dst[i] = from_f<Dt>(to_f<S>(src[i]));
+  }
+}
+
+template <typename S>
+int cast_from(const void* src, void* dst, int dd, long long n, cudaStream_t st) {
+  const int threads = 256;
+  const long long blocks = (n + threads * 4 - 1) / (threads * 4);
+  if (dd == GOAT_F32) cast_kernel<S, float><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (float*)dst, n);
+  else if (dd == GOAT_F16) cast_kernel<S, __half><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (__half*)dst, n);
+  else cast_kernel<S, __nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (__nv_bfloat16*)dst, n);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+}  // namespace
+}  // namespace goat
+
+using namespace goat;
+
+extern "C" int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps,
+                                  float* y32, void* y16, int y16_dtype, float* mean, float* rstd, int M, int H,
+                                  goat_stream_t stream) {
+  GOAT_CHECK(x && gamma && beta, "goat_layernorm_fwd: null x/gamma/beta");
+  GOAT_CHECK(y32 || y16, "goat_layernorm_fwd: no output requested");
+  GOAT_CHECK(H > 0 && H <= 32 * LN_MAX_PER_LANE, "goat_layernorm_fwd: H=%d unsupported (max %d)", H, 32 * LN_MAX_PER_LANE);
+  GOAT_CHECK(!y16 || y16_dtype == GOAT_F16 || y16_dtype == GOAT_BF16, "goat_layernorm_fwd: y16 dtype must be F16/BF16");
+  if (M <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((M + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA);
+#define LN_FWD(TX, TY) ln_fwd_kernel<TX, TY><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M, H)
+  const bool yh = (y16_dtype == GOAT_F16);
+  if (x_dtype == GOAT_F32) { if (yh) LN_FWD(float, __half); else LN_FWD(float, __nv_bfloat16); }
+  else if (x_dtype == GOAT_F16) { if (yh) LN_FWD(__half, __half); else LN_FWD(__half, __nv_bfloat16); }
+  else if (x_dtype == GOAT_BF16) { if (yh) LN_FWD(__nv_bfloat16, __half); else LN_FWD(__nv_bfloat16, __nv_bfloat16); }
+  else GOAT_CHECK(false, "goat_layernorm_fwd: bad x dtype");
+#undef LN_FWD
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" size_t goat_layernorm_bwd_workspace_bytes(int M, int H) {
+  return (size_t)ln_bwd_parts(M) * 3 * (size_t)H * sizeof(float);
+}
+
+extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
+                                  const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype,
+                                  float drop_p, uint64_t drop_seed, float* dgamma, float* dbeta, float* dcolsum,
+                                  void* workspace, int M, int H, goat_stream_t stream) {
+  GOAT_CHECK(dy && x && gamma && mean && rstd && workspace, "goat_layernorm_bwd: null argument");
+  GOAT_CHECK(H > 0 && H <= 32 * LN_MAX_PER_LANE, "goat_layernorm_bwd: H=%d unsupported", H);
+  GOAT_CHECK(!dx16 || dx16_dtype == GOAT_F16 || dx16_dtype == GOAT_BF16, "goat_layernorm_bwd: dx16 dtype must be F16/BF16");
+  GOAT_CHECK(drop_p >= 0.f && drop_p < 1.f, "goat_layernorm_bwd: drop_p out of range");
+  if (M <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int parts = ln_bwd_parts(M);
+  const int rows_per_cta = (M + parts - 1) / parts;
+  const size_t smem = (size_t)4 * 3 * H * sizeof(float);
+  float* partial = reinterpret_cast<float*>(workspace);
+#define LN_BWD(TX, TD)                                                                                                \
+  do {                                                                                                                \
+    static bool cfg = false;                                                                                          \
+    if (!cfg && smem > 48 * 1024) {                                                                                   \
+      GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<TX, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 1024 * 4)); \
+      cfg = true;                                                                                                     \
+    }                                                                                                                 \
+    ln_bwd_kernel<TX, TD><<<parts, 128, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx32, dx16, drop_p, drop_seed,    \
+                                                    partial, M, H, rows_per_cta);                                     \
+  } while (0)
+  const bool dh = (dx16_dtype == GOAT_F16);
+  if (x_dtype == GOAT_F32) { if (dh) LN_BWD(float, __half); else LN_BWD(float, __nv_bfloat16); }
+  else if (x_dtype == GOAT_F16) { if (dh) LN_BWD(__half, __half); else LN_BWD(__half, __nv_bfloat16); }
+  else if (x_dtype == GOAT_BF16) { if (dh) LN_BWD(__nv_bfloat16, __half); else LN_BWD(__nv_bfloat16, __nv_bfloat16); }
+  else GOAT_CHECK(false, "goat_layernorm_bwd: bad x dtype");
+#undef LN_BWD
+  GOAT_LAUNCH_CHECK();
+  ln_bwd_finalize_kernel<<<(H + 127) / 128, 128, 0, st>>>(partial, parts, H, dgamma, dbeta, dcolsum);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" size_t goat_colsum_workspace_bytes(int M, int N) { return (size_t)colsum_parts(M) * (size_t)N * sizeof(float); }
+
+extern "C" int goat_colsum(const void* x, int dtype, int M, int N, int ld, float* out, void* workspace,
+                           goat_stream_t stream) {
+  GOAT_CHECK(x && out && workspace, "goat_colsum: null argument");
+  GOAT_CHECK(N > 0 && ld >= N, "goat_colsum: bad N/ld");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 0) {
+    GOAT_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
+    return GOAT_OK;
+  }
+  const int parts = colsum_parts(M);
+  const int rows_per_cta = (M + parts - 1) / parts;
+  dim3 grid((N + 255) / 256, parts);
+  float* partial = reinterpret_cast<float*>(workspace);
+  if (dtype == GOAT_F32) colsum_partial_kernel<float><<<grid, 256, 0, st>>>(x, M, N, ld, rows_per_cta, partial);
+  else if (dtype == GOAT_F16) colsum_partial_kernel<__half><<<grid, 256, 0, st>>>(x, M, N, ld, rows_per_cta, partial);
+  else if (dtype == GOAT_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, M, N, ld, rows_per_cta, partial);
+  else GOAT_CHECK(false, "goat_colsum: bad dtype");
+  GOAT_LAUNCH_CHECK();
+  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, parts, N, out);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, goat_stream_t stream) {
+  GOAT_CHECK(src && dst, "goat_cast: null argument");
+  if (n <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (src_dtype == GOAT_F32) return cast_from<float>(src, dst, dst_dtype, n, st);
+  if (src_dtype == GOAT_F16) return cast_from<__half>(src, dst, dst_dtype, n, st);
+  if (src_dtype == GOAT_BF16) return cast_from<__nv_bfloat16>(src, dst, dst_dtype, n, st);
+  GOAT_CHECK(false, "goat_cast: bad dtype");
+}

@@ -1,0 +1,206 @@
+"""Thin tensor-level wrappers around the C ABI (no autograd here; see functional.py).
+
+Everything takes CUDA tensors, enqueues on torch's current stream, and allocates outputs /
+workspaces through torch's caching allocator (the library itself allocates nothing).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F16, F32  # noqa: F401
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+def dt(t):
+    try:
+        return _DT[t if isinstance(t, torch.dtype) else t.dtype]
+    except KeyError:
+        raise TypeError("unsupported dtype %s" % (t if isinstance(t, torch.dtype) else t.dtype))
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vln_goat_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _rowmajor2d(t, name):
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("%s must be 2-D with unit inner stride, got shape %s strides %s" % (name, tuple(t.shape), t.stride()))
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_out=None, out=None, out_dtype=None,
+         out2=None, act=ACT_NONE, alpha=1.0, drop_p=0.0, drop_seed=0, force_simt=False):
+    """out[M,N] = epilogue(alpha * A B^T).  A: [M,K] (a_mn False) or [K,M] (a_mn True);
+    B: [N,K] (b_mn False) or [K,N] (b_mn True).  See goat_gemm in include/goat_sm100.h."""
+    _req_cuda(A, B, bias, res, aux_in, aux_out, out, out2)
+    lda = _rowmajor2d(A, "A")
+    ldb = _rowmajor2d(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn else (B.shape[0], B.shape[1])
+    if K != Kb or A.dtype != B.dtype:
+        raise ValueError("gemm: A %s / B %s mismatch" % (tuple(A.shape), tuple(B.shape)))
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=out_dtype or A.dtype)
+    a = _lib.GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.dtype = dt(A)
+    a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
+    a.lda, a.ldb = lda, ldb
+    a.A, a.B = A.data_ptr(), B.data_ptr()
+    a.bias = None if bias is None else bias.data_ptr()
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm: bias must be contiguous fp32 [N]")
+    if res is not None:
+        if res.dtype != torch.float32 or tuple(res.shape) != (M, N):
+            raise ValueError("gemm: res must be fp32 [M,N]")
+        a.res, a.ldres = res.data_ptr(), _rowmajor2d(res, "res")
+    for name, t in (("aux_in", aux_in), ("aux_out", aux_out)):
+        if t is not None:
+            if t.dtype != A.dtype or tuple(t.shape) != (M, N):
+                raise ValueError("gemm: %s must have the operand dtype and shape [M,N]" % name)
+            setattr(a, name, t.data_ptr())
+            a.ldaux = _rowmajor2d(t, name)
+    if tuple(out.shape) != (M, N):
+        raise ValueError("gemm: out shape %s != (%d,%d)" % (tuple(out.shape), M, N))
+    a.out, a.ldc, a.out_dtype = out.data_ptr(), _rowmajor2d(out, "out"), dt(out)
+    if out2 is not None:
+        if out2.dtype != A.dtype or tuple(out2.shape) != (M, N):
+            raise ValueError("gemm: out2 must have the operand dtype and shape [M,N]")
+        a.out2, a.ldc2 = out2.data_ptr(), _rowmajor2d(out2, "out2")
+    a.act, a.alpha, a.drop_p, a.drop_seed = act, alpha, drop_p, drop_seed
+    a.force_simt = int(force_simt)
+    _lib.check(_lib.lib().goat_gemm(C.byref(a), _stream()), "goat_gemm")
+    return out
+
+
+def _tok3(t, name, heads):
+    """[B, N, >=heads*64] view with unit inner stride -> (ld, sb)."""
+    if t.dim() != 3 or t.stride(2) != 1 or t.shape[2] != heads * 64:
+        raise ValueError("%s must be [B,N,heads*64] with unit inner stride, got %s / %s" % (name, tuple(t.shape), t.stride()))
+    return t.stride(1), t.stride(0)
+
+
+def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed):
+    B, Nq, _ = q.shape
+    Nk = k.shape[1]
+    a = _lib.AttnArgs()
+    a.B, a.heads, a.Nq, a.Nk, a.D = B, heads, Nq, Nk, 64
+    a.dtype = dt(q)
+    a.Q, a.K, a.V, a.O = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.ldq, a.sbq = _tok3(q, "q", heads)
+    a.ldk, a.sbk = _tok3(k, "k", heads)
+    a.ldv, a.sbv = _tok3(v, "v", heads)
+    a.ldo, a.sbo = _tok3(o, "o", heads)
+    if kmask is not None:
+        if kmask.dtype != torch.float32 or tuple(kmask.shape) != (B, Nk) or not kmask.is_contiguous():
+            raise ValueError("attn: kmask must be contiguous fp32 [B,Nk]")
+        a.kmask = kmask.data_ptr()
+    if bias is not None:
+        if bias.dtype != torch.float32 or tuple(bias.shape) != (B, Nq, Nk) or not bias.is_contiguous():
+            raise ValueError("attn: bias must be contiguous fp32 [B,Nq,Nk]")
+        a.bias = bias.data_ptr()
+    a.scale = scale
+    a.lse = lse.data_ptr()
+    a.drop_p, a.drop_seed = drop_p, drop_seed
+    return a
+
+
+def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0):
+    """-> (O [B,Nq,heads*64] same dtype, lse [B,heads,Nq] fp32)"""
+    _req_cuda(q, k, v, kmask, bias)
+    B, Nq, _ = q.shape
+    o = torch.empty((B, Nq, heads * 64), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, heads, Nq), device=q.device, dtype=torch.float32)
+    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed)
+    _lib.check(_lib.lib().goat_attn_core_fwd(C.byref(a), _stream()), "goat_attn_core_fwd")
+    return o, lse
+
+
+def attn_bwd(do, q, k, v, o, lse, heads, dq, dk, dv, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0,
+             want_dbias=False):
+    """dq/dk/dv: preallocated views with the same strides as q/k/v.  -> dbias [B,Nq,Nk] fp32 or None"""
+    _req_cuda(do, q, k, v, o, lse, dq, dk, dv)
+    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed)
+    for name, t, ref in (("dq", dq, q), ("dk", dk, k), ("dv", dv, v), ("do", do, o)):
+        if t.stride() != ref.stride() or t.shape != ref.shape or t.dtype != ref.dtype:
+            raise ValueError("attn_bwd: %s must match the layout of its forward tensor" % name)
+    a.dO, a.dQ, a.dK, a.dV = do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    dbias = None
+    if want_dbias:
+        dbias = torch.zeros((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
+        a.dbias = dbias.data_ptr()
+    _lib.check(_lib.lib().goat_attn_core_bwd(C.byref(a), _stream()), "goat_attn_core_bwd")
+    return dbias
+
+
+def layernorm_fwd(x, gamma, beta, eps, want32=True, dtype16=None):
+    """x [M,H] contiguous -> (y32 or None, y16 or None, mean [M], rstd [M])"""
+    _req_cuda(x, gamma, beta)
+    if x.dim() != 2 or not x.is_contiguous():
+        raise ValueError("layernorm_fwd: x must be contiguous [M,H]")
+    M, H = x.shape
+    y32 = torch.empty((M, H), device=x.device, dtype=torch.float32) if want32 else None
+    y16 = torch.empty((M, H), device=x.device, dtype=dtype16) if dtype16 is not None else None
+    mean = torch.empty((M,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((M,), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().goat_layernorm_fwd(_p(x), dt(x), _p(gamma), _p(beta), eps, _p(y32), _p(y16),
+                                       dt(dtype16) if dtype16 is not None else F16, _p(mean), _p(rstd), M, H, _stream())
+    _lib.check(rc, "goat_layernorm_fwd")
+    return y32, y16, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None, drop_p=0.0, drop_seed=0,
+                  want_colsum=False):
+    """-> (dx32 or None, dx16 or None, dgamma [H], dbeta [H], dcolsum [H] or None)"""
+    _req_cuda(dy, x, gamma, mean, rstd, dres)
+    M, H = x.shape
+    if dy.dtype != torch.float32 or not dy.is_contiguous() or tuple(dy.shape) != (M, H):
+        raise ValueError("layernorm_bwd: dy must be contiguous fp32 [M,H]")
+    dev = x.device
+    dx32 = torch.empty((M, H), device=dev, dtype=torch.float32) if want32 else None
+    dx16 = torch.empty((M, H), device=dev, dtype=dtype16) if dtype16 is not None else None
+    dgamma = torch.empty((H,), device=dev, dtype=torch.float32)
+    dbeta = torch.empty((H,), device=dev, dtype=torch.float32)
+    dcol = torch.empty((H,), device=dev, dtype=torch.float32) if want_colsum else None
+    ws = torch.empty((_lib.lib().goat_layernorm_bwd_workspace_bytes(M, H),), device=dev, dtype=torch.uint8)
+    rc = _lib.lib().goat_layernorm_bwd(_p(dy), _p(x), dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
+                                       dt(dtype16) if dtype16 is not None else F16, drop_p, drop_seed, _p(dgamma),
+                                       _p(dbeta), _p(dcol), _p(ws), M, H, _stream())
+    _lib.check(rc, "goat_layernorm_bwd")
+    return dx32, dx16, dgamma, dbeta, dcol
+
+
+def colsum(x):
+    """x [M,N] (unit inner stride) -> fp32 [N]"""
+    _req_cuda(x)
+    ld = _rowmajor2d(x, "x")
+    M, N = x.shape
+    out = torch.empty((N,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((_lib.lib().goat_colsum_workspace_bytes(M, N),), device=x.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().goat_colsum(_p(x), dt(x), M, N, ld, _p(out), _p(ws), _stream()), "goat_colsum")
+    return out
+
+
+def cast(src, dtype, out=None):
+    """contiguous tensor -> new tensor (or `out`) of `dtype`"""
+    _req_cuda(src, out)
+    if not src.is_contiguous():
+        raise ValueError("cast: src must be contiguous")
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=dtype)
+    elif not out.is_contiguous() or out.numel() != src.numel():
+        raise ValueError("cast: bad out")
+    _lib.check(_lib.lib().goat_cast(_p(src), dt(src), _p(out), dt(out), src.numel(), _stream()), "goat_cast")
+    return out
