@@ -86,6 +86,7 @@ typedef struct goat_gemm_args {
   float alpha;
   float drop_p;
   uint64_t drop_seed;
+  const uint64_t* drop_seed_ptr; /* optional DEVICE word added to drop_seed at run time (CUDA-graph safe reseeding) */
   int force_simt;
 } goat_gemm_args;
 int goat_gemm(const goat_gemm_args* args, goat_stream_t stream);
@@ -120,6 +121,7 @@ typedef struct goat_attn_args {
   float* lse; /* [B, heads, Nq] */
   float drop_p;
   uint64_t drop_seed;
+  const uint64_t* drop_seed_ptr; /* optional DEVICE word added to drop_seed at run time */
   /* backward only */
   const void* dO; /* same layout as O */
   void* dQ;       /* same layout as Q (ldq, sbq) */
@@ -137,9 +139,10 @@ int goat_attn_core_bwd(const goat_attn_args* args, goat_stream_t stream);
  * reference (:309) is fused into the producing goat_gemm epilogue (res).
  * fwd: x [M,H] (x_dtype) -> y32 (fp32, optional) and/or y16 (y16_dtype, optional); mean/rstd [M].
  * bwd: dy [M,H] fp32 (+ optional dy2 fp32 added to it) -> dx32 = LN'(dy) (+ dres if given),
- *      dx16 (optional 16-bit copy of the LN' term only, masked by dropout(drop_p, seed) for the
- *      GEMM that produced x), dgamma/dbeta [H] (written, not accumulated), dcolsum [H] optional =
- *      column sum of the dx16 values (the bias gradient of the producing Linear).
+ *      dx16 (optional copy, dtype dx16_dtype = F16/BF16/F32, of the LN' term only, masked by
+ *      dropout(drop_p, seed) for the GEMM that produced x), dgamma/dbeta [H] (written, not
+ *      accumulated), dcolsum [H] optional = column sum of the dx16 values (the bias gradient of the
+ *      producing Linear).
  *      workspace: goat_layernorm_bwd_workspace_bytes(M, H).
  * ------------------------------------------------------------------------------------------ */
 int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, float* y32,
@@ -147,8 +150,8 @@ int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const flo
 size_t goat_layernorm_bwd_workspace_bytes(int M, int H);
 int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
                        const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype, float drop_p,
-                       uint64_t drop_seed, float* dgamma, float* dbeta, float* dcolsum, void* workspace, int M, int H,
-                       goat_stream_t stream);
+                       uint64_t drop_seed, const uint64_t* drop_seed_ptr, float* dgamma, float* dbeta, float* dcolsum,
+                       void* workspace, int M, int H, goat_stream_t stream);
 
 /* column sum: out[n] = sum_m x[m*ld + n]  (bias gradients).  workspace: goat_colsum_workspace_bytes(M,N) */
 size_t goat_colsum_workspace_bytes(int M, int N);
@@ -156,6 +159,10 @@ int goat_colsum(const void* x, int dtype, int M, int N, int ld, float* out, void
 
 /* dtype conversion of n contiguous elements (fp32 master weights -> 16-bit operands, activations in/out) */
 int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, goat_stream_t stream);
+/* same, with the dropout mask of element index i = 0..n-1 applied (regenerates the mask a goat_gemm epilogue
+ * used on a contiguous [M,N] output: index m*N+n).  Backward of the pre-LN pano layers (P/model/transformer.py:170-182). */
+int goat_dropout_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float drop_p,
+                      uint64_t drop_seed, const uint64_t* drop_seed_ptr, goat_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldc", C.c_int), ("out_dtype", C.c_int),
         ("out2", C.c_void_p), ("ldc2", C.c_int),
         ("act", C.c_int), ("alpha", C.c_float), ("drop_p", C.c_float),
-        ("drop_seed", C.c_uint64),
+        ("drop_seed", C.c_uint64), ("drop_seed_ptr", C.c_void_p),
         ("force_simt", C.c_int),
     ]
 
@@ -42,7 +42,7 @@ class AttnArgs(C.Structure):
         ("scale", C.c_float),
         ("O", C.c_void_p), ("ldo", C.c_int), ("sbo", C.c_longlong),
         ("lse", C.c_void_p),
-        ("drop_p", C.c_float), ("drop_seed", C.c_uint64),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint64), ("drop_seed_ptr", C.c_void_p),
         ("dO", C.c_void_p), ("dQ", C.c_void_p), ("dK", C.c_void_p), ("dV", C.c_void_p),
         ("dbias", C.c_void_p),
     ]
@@ -61,10 +61,12 @@ SYMBOLS = {
     "goat_layernorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "goat_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "goat_colsum_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "goat_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "goat_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "goat_dropout_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint64,
+                                    C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

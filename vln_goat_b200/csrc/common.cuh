@@ -126,7 +126,12 @@ struct EpiParams {
   float alpha;           // scales the accumulator before bias
   float drop_p;          // dropout probability applied after activation, before residual (0 = off)
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_ptr;  // optional device word added to drop_seed
 };
+
+__device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed, const unsigned long long* ptr) {
+  return ptr ? seed + *ptr : seed;
+}
 
 template <typename T>
 __device__ __forceinline__ float epi_apply(const EpiParams& ep, int m, int n, float acc) {
@@ -147,7 +152,8 @@ __device__ __forceinline__ float epi_apply(const EpiParams& ep, int m, int n, fl
     v = tanhf(v);
   }
   if (ep.drop_p > 0.0f) {
-    const float u = rand_uniform(ep.drop_seed, (unsigned long long)m * (unsigned long long)ep.ldc + n);
+    const float u = rand_uniform(eff_seed(ep.drop_seed, ep.drop_seed_ptr),
+                                 (unsigned long long)m * (unsigned long long)ep.ldc + n);
     v = (u >= ep.drop_p) ? v * (1.0f / (1.0f - ep.drop_p)) : 0.0f;
   }
   if (ep.res) v += ep.res[(size_t)m * ep.ldres + n];

@@ -187,9 +187,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (ep.drop_p > 0.0f) {
           const float keep = 1.0f / (1.0f - ep.drop_p);
+          const unsigned long long seed = eff_seed(ep.drop_seed, ep.drop_seed_ptr);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float u = rand_uniform(ep.drop_seed, (unsigned long long)row * (unsigned long long)ep.ldc + nc + j);
+            const float u = rand_uniform(seed, (unsigned long long)row * (unsigned long long)ep.ldc + nc + j);
             v[j] = (u >= ep.drop_p) ? v[j] * keep : 0.0f;
           }
         }

@@ -69,8 +69,9 @@ template <typename TX, typename TD>
 __global__ void __launch_bounds__(128)
 ln_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
-              float* __restrict__ dx32, void* __restrict__ dx16, float drop_p, unsigned long long drop_seed,
-              float* __restrict__ partial, int M, int H, int rows_per_cta) {
+              float* __restrict__ dx32, void* __restrict__ dx16, float drop_p, unsigned long long drop_seed_,
+              const unsigned long long* __restrict__ drop_seed_ptr, float* __restrict__ partial, int M, int H,
+              int rows_per_cta) {
   extern __shared__ float sacc[];  // [4 warps][3][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = (H + 31) / 32;
@@ -80,6 +81,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x, const fl
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(M, r0 + rows_per_cta);
   const float keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const unsigned long long drop_seed = drop_p > 0.f ? eff_seed(drop_seed_, drop_seed_ptr) : 0ull;
   for (int row = r0 + warp; row < r1; row += 4) {
     const float mu = mean[row], rs = rstd[row];
     float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
@@ -190,23 +192,32 @@ inline int colsum_parts(int M) {
 
 // ---------------------------------------------------------------------------------------------
 template <typename S, typename Dt>
-__global__ void cast_kernel(const S* __restrict__ src, Dt* __restrict__ dst, long long n) {
+__global__ void cast_kernel(const S* __restrict__ src, Dt* __restrict__ dst, long long n, float drop_p,
+                            unsigned long long drop_seed_, const unsigned long long* __restrict__ drop_seed_ptr) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i + 3 < n) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dst[i + j] = from_f<Dt>(to_f<S>(src[i + j]));
+  const long long e = i + 4 < n ? i + 4 : n;
+  if (drop_p > 0.f) {
+    const unsigned long long seed = eff_seed(drop_seed_, drop_seed_ptr);
+    const float keep = 1.f / (1.f - drop_p);
+    for (; i < e; ++i)
+      dst[i] = from_f<Dt>(rand_uniform(seed, (unsigned long long)i) >= drop_p ? to_f<S>(src[i]) * keep : 0.f);
   } else {
-    for (; i < n; ++i) dst[i] = from_f<Dt>(to_f<S>(src[i]));
+    for (; i < e; ++i) dst[i] = from_f<Dt>(to_f<S>(src[i]));
   }
 }
 
 template <typename S>
-int cast_from(const void* src, void* dst, int dd, long long n, cudaStream_t st) {
+int cast_from(const void* src, void* dst, int dd, long long n, float p, unsigned long long seed,
+              const unsigned long long* seed_ptr, cudaStream_t st) {
   const int threads = 256;
   const long long blocks = (n + threads * 4 - 1) / (threads * 4);
-  if (dd == GOAT_F32) cast_kernel<S, float><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (float*)dst, n);
-  else if (dd == GOAT_F16) cast_kernel<S, __half><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (__half*)dst, n);
-  else cast_kernel<S, __nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (__nv_bfloat16*)dst, n);
+  if (dd == GOAT_F32)
+    cast_kernel<S, float><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (float*)dst, n, p, seed, seed_ptr);
+  else if (dd == GOAT_F16)
+    cast_kernel<S, __half><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (__half*)dst, n, p, seed, seed_ptr);
+  else if (dd == GOAT_BF16)
+    cast_kernel<S, __nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>((const S*)src, (__nv_bfloat16*)dst, n, p, seed, seed_ptr);
+  else GOAT_CHECK(false, "goat_cast: bad dst dtype");
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
@@ -243,11 +254,12 @@ extern "C" size_t goat_layernorm_bwd_workspace_bytes(int M, int H) {
 
 extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
                                   const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype,
-                                  float drop_p, uint64_t drop_seed, float* dgamma, float* dbeta, float* dcolsum,
-                                  void* workspace, int M, int H, goat_stream_t stream) {
+                                  float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_ptr, float* dgamma,
+                                  float* dbeta, float* dcolsum, void* workspace, int M, int H, goat_stream_t stream) {
   GOAT_CHECK(dy && x && gamma && mean && rstd && workspace, "goat_layernorm_bwd: null argument");
   GOAT_CHECK(H > 0 && H <= 32 * LN_MAX_PER_LANE, "goat_layernorm_bwd: H=%d unsupported", H);
-  GOAT_CHECK(!dx16 || dx16_dtype == GOAT_F16 || dx16_dtype == GOAT_BF16, "goat_layernorm_bwd: dx16 dtype must be F16/BF16");
+  GOAT_CHECK(!dx16 || dx16_dtype == GOAT_F16 || dx16_dtype == GOAT_BF16 || dx16_dtype == GOAT_F32,
+             "goat_layernorm_bwd: bad dx16 dtype");
   GOAT_CHECK(drop_p >= 0.f && drop_p < 1.f, "goat_layernorm_bwd: drop_p out of range");
   if (M <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -263,13 +275,21 @@ extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, c
       cfg = true;                                                                                                     \
     }                                                                                                                 \
     ln_bwd_kernel<TX, TD><<<parts, 128, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx32, dx16, drop_p, drop_seed,    \
+                                                    reinterpret_cast<const unsigned long long*>(drop_seed_ptr),      \
                                                     partial, M, H, rows_per_cta);                                     \
   } while (0)
-  const bool dh = (dx16_dtype == GOAT_F16);
-  if (x_dtype == GOAT_F32) { if (dh) LN_BWD(float, __half); else LN_BWD(float, __nv_bfloat16); }
-  else if (x_dtype == GOAT_F16) { if (dh) LN_BWD(__half, __half); else LN_BWD(__half, __nv_bfloat16); }
-  else if (x_dtype == GOAT_BF16) { if (dh) LN_BWD(__nv_bfloat16, __half); else LN_BWD(__nv_bfloat16, __nv_bfloat16); }
+  const int dd = dx16 ? dx16_dtype : GOAT_F16;
+#define LN_BWD_X(TX)                                                      \
+  do {                                                                    \
+    if (dd == GOAT_F16) LN_BWD(TX, __half);                               \
+    else if (dd == GOAT_BF16) LN_BWD(TX, __nv_bfloat16);                  \
+    else LN_BWD(TX, float);                                               \
+  } while (0)
+  if (x_dtype == GOAT_F32) LN_BWD_X(float);
+  else if (x_dtype == GOAT_F16) LN_BWD_X(__half);
+  else if (x_dtype == GOAT_BF16) LN_BWD_X(__nv_bfloat16);
   else GOAT_CHECK(false, "goat_layernorm_bwd: bad x dtype");
+#undef LN_BWD_X
 #undef LN_BWD
   GOAT_LAUNCH_CHECK();
   ln_bwd_finalize_kernel<<<(H + 127) / 128, 128, 0, st>>>(partial, parts, H, dgamma, dbeta, dcolsum);
@@ -302,12 +322,19 @@ extern "C" int goat_colsum(const void* x, int dtype, int M, int N, int ld, float
   return GOAT_OK;
 }
 
-extern "C" int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, goat_stream_t stream) {
+extern "C" int goat_dropout_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float drop_p,
+                                 uint64_t drop_seed, const uint64_t* drop_seed_ptr, goat_stream_t stream) {
   GOAT_CHECK(src && dst, "goat_cast: null argument");
+  GOAT_CHECK(drop_p >= 0.f && drop_p < 1.f, "goat_dropout_cast: drop_p out of range");
   if (n <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (src_dtype == GOAT_F32) return cast_from<float>(src, dst, dst_dtype, n, st);
-  if (src_dtype == GOAT_F16) return cast_from<__half>(src, dst, dst_dtype, n, st);
-  if (src_dtype == GOAT_BF16) return cast_from<__nv_bfloat16>(src, dst, dst_dtype, n, st);
-  GOAT_CHECK(false, "goat_cast: bad dtype");
+  const unsigned long long* sp = reinterpret_cast<const unsigned long long*>(drop_seed_ptr);
+  if (src_dtype == GOAT_F32) return cast_from<float>(src, dst, dst_dtype, n, drop_p, drop_seed, sp, st);
+  if (src_dtype == GOAT_F16) return cast_from<__half>(src, dst, dst_dtype, n, drop_p, drop_seed, sp, st);
+  if (src_dtype == GOAT_BF16) return cast_from<__nv_bfloat16>(src, dst, dst_dtype, n, drop_p, drop_seed, sp, st);
+  GOAT_CHECK(false, "goat_cast: bad src dtype");
+}
+
+extern "C" int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, goat_stream_t stream) {
+  return goat_dropout_cast(src, src_dtype, dst, dst_dtype, n, 0.f, 0, nullptr, stream);
 }

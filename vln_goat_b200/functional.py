@@ -1,0 +1,305 @@
+"""Autograd composites over the C-ABI primitives: one Function per transformer block.
+
+Every Function works on 2-D token-major activations [tokens, hidden].  The residual stream stays
+fp32 (``x32``); GEMM operands are the compute dtype (fp16 / bf16 copies written by the LayerNorm
+kernel, or the fp32 tensor itself in fp32 parity mode).  Backward passes are hand-written from the
+same primitives (dgrad / wgrad GEMMs with MN-major operands, recompute-based attention backward).
+
+Reference semantics (P/ = pretrain_src/, M/ = map_nav_src/ of CrystalSixone/VLN-GOAT):
+  AttnBlockFn  = BertAttention / RobertaAttention        P/model/Bert_backbone.py:199-342, :387-543
+  FFNBlockFn   = BertIntermediate + BertOutput           P/model/Bert_backbone.py:345-370
+  PanoLayerFn  = TransformerEncoderLayer.forward_pre     P/model/transformer.py:170-182
+  LinearFn     = nn.Linear (+ ReLU / tanh / GELU)        heads, poolers, position embeddings
+  LayerNormFn  = nn.LayerNorm
+"""
+import itertools
+from collections import namedtuple
+
+import torch
+
+from . import ops
+
+_seed_counter = itertools.count(1)
+
+
+def next_seed():
+    """A fresh host-side dropout seed (kernels add the optional device-side step counter to it)."""
+    return (next(_seed_counter) * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF
+
+
+def _c(x32, x16, cdt):
+    """compute-dtype view of an activation: fp32 mode uses the fp32 tensor itself"""
+    if cdt == torch.float32:
+        return x32
+    if x16 is not None:
+        return x16
+    return ops.cast(x32, cdt)
+
+
+def _d16(cdt):
+    return None if cdt == torch.float32 else cdt
+
+
+def _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, p, seed, seed_ptr):
+    """LN backward of a post-LN block: (residual-path grad fp32, GEMM-operand grad in the compute dtype with the
+    hidden-dropout mask applied, dgamma, dbeta, bias grad of the producing Linear)."""
+    if cdt == torch.float32 and p == 0.0:
+        d32, _, dg, db, dcol = ops.layernorm_bwd(dy32, pre, gamma, mean, rstd, None, True, None, want_colsum=True)
+        return d32, d32, dg, db, dcol
+    return ops.layernorm_bwd(dy32, pre, gamma, mean, rstd, None, True, cdt, p, seed, seed_ptr, want_colsum=True)
+
+
+AttnCfg = namedtuple("AttnCfg", "B Nq Nk heads eps attn_p hid_p seed seed_ptr cross cdt")
+
+
+class AttnBlockFn(torch.autograd.Function):
+    """y = LN(dropout(ctx W_o^T + b_o) + x),  ctx = softmax(q k^T / 8 + kmask + bias) v
+    self-attention: q,k,v from x (one fused [3H,H] projection); cross: q from x, k,v from kv."""
+
+    @staticmethod
+    def forward(ctx, x32, x16, kv32, kv16, kmask, bias, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, Wqkv_c, bqkv,
+                Wo_c, cfg):
+        H = x32.shape[1]
+        cdt = cfg.cdt
+        xc = _c(x32, x16, cdt)
+        if not cfg.cross:
+            qkv = ops.gemm(xc, Wqkv_c, bias=bqkv, out_dtype=cdt)                   # [M,3H]
+            q2, k2, v2 = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+            kvc = None
+            kvp = None
+        else:
+            kvc = _c(kv32, kv16, cdt)
+            q2 = ops.gemm(xc, Wqkv_c[:H], bias=bqkv[:H], out_dtype=cdt)            # [M,H]
+            kvp = ops.gemm(kvc, Wqkv_c[H:], bias=bqkv[H:], out_dtype=cdt)          # [Mk,2H]
+            k2, v2 = kvp[:, :H], kvp[:, H:]
+            qkv = q2
+        B, Nq, Nk = cfg.B, cfg.Nq, cfg.Nk
+        q3 = q2.unflatten(0, (B, Nq))
+        k3 = k2.unflatten(0, (B, Nk))
+        v3 = v2.unflatten(0, (B, Nk))
+        o3, lse = ops.attn_fwd(q3, k3, v3, cfg.heads, kmask, bias, 0.125, cfg.attn_p, cfg.seed, cfg.seed_ptr)
+        o2 = o3.view(B * Nq, H)
+        pre = ops.gemm(o2, Wo_c, bias=bo, res=x32, out_dtype=torch.float32, drop_p=cfg.hid_p, drop_seed=cfg.seed + 1,
+                       seed_ptr=cfg.seed_ptr)
+        y32, y16, mean, rstd = ops.layernorm_fwd(pre, gamma, beta, cfg.eps, True, _d16(cdt))
+        ctx.cfg = cfg
+        ctx.save_for_backward(xc, kvc, qkv, kvp, o2, lse, pre, mean, rstd, kmask, bias, Wqkv_c, Wo_c, gamma)
+        if y16 is not None:
+            ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, _dy16):
+        cfg = ctx.cfg
+        xc, kvc, qkv, kvp, o2, lse, pre, mean, rstd, kmask, bias, Wqkv_c, Wo_c, gamma = ctx.saved_tensors
+        cdt = cfg.cdt
+        H = pre.shape[1]
+        B, Nq, Nk = cfg.B, cfg.Nq, cfg.Nk
+        dy32 = dy32.contiguous()
+        # LN backward: dpre32 feeds the residual path, dpre_c (dropout-masked) feeds the out-proj GEMMs
+        dpre32, dpre_c, dgamma, dbeta, dbo = _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, cfg.hid_p, cfg.seed + 1,
+                                                           cfg.seed_ptr)
+        dWo = ops.gemm(dpre_c, o2, a_mn=True, b_mn=True, out_dtype=torch.float32)          # [H,H]
+        do2 = ops.gemm(dpre_c, Wo_c, b_mn=True, out_dtype=cdt)                              # [M,H]
+        want_dbias = bias is not None and ctx.needs_input_grad[5]
+        if not cfg.cross:
+            dqkv = torch.empty_like(qkv)
+            q2, k2, v2 = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+            dq2, dk2, dv2 = dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]
+        else:
+            dqkv = torch.empty_like(qkv)          # dq only
+            dkvp = torch.empty_like(kvp)
+            q2, k2, v2 = qkv, kvp[:, :H], kvp[:, H:]
+            dq2, dk2, dv2 = dqkv, dkvp[:, :H], dkvp[:, H:]
+        dbias = ops.attn_bwd(do2.view(B, Nq, H), q2.unflatten(0, (B, Nq)), k2.unflatten(0, (B, Nk)),
+                             v2.unflatten(0, (B, Nk)), o2.view(B, Nq, H), lse, cfg.heads,
+                             dq2.unflatten(0, (B, Nq)), dk2.unflatten(0, (B, Nk)), dv2.unflatten(0, (B, Nk)),
+                             kmask, bias, 0.125, cfg.attn_p, cfg.seed, cfg.seed_ptr, want_dbias=want_dbias)
+        dkv32 = None
+        if not cfg.cross:
+            dW = ops.gemm(dqkv, xc, a_mn=True, b_mn=True, out_dtype=torch.float32)          # [3H,H]
+            db = ops.colsum(dqkv)
+            dx32 = ops.gemm(dqkv, Wqkv_c, b_mn=True, res=dpre32, out_dtype=torch.float32)   # [M,H]
+        else:
+            dW = torch.empty((3 * H, H), device=xc.device, dtype=torch.float32)
+            db = torch.empty((3 * H,), device=xc.device, dtype=torch.float32)
+            ops.gemm(dqkv, xc, a_mn=True, b_mn=True, out=dW[:H])                             # dWq  [H,H]
+            ops.gemm(dkvp, kvc, a_mn=True, b_mn=True, out=dW[H:])                            # dWkv [2H,H]
+            ops.colsum(dqkv, out=db[:H])
+            ops.colsum(dkvp, out=db[H:])
+            dx32 = ops.gemm(dqkv, Wqkv_c[:H], b_mn=True, res=dpre32, out_dtype=torch.float32)
+            if ctx.needs_input_grad[2]:
+                dkv32 = ops.gemm(dkvp, Wqkv_c[H:], b_mn=True, out_dtype=torch.float32)      # [Mk,H]
+        return (dx32, None, dkv32, None, None, dbias, dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:],
+                dWo, dbo, dgamma, dbeta, None, None, None, None)
+
+
+FFNCfg = namedtuple("FFNCfg", "eps hid_p seed seed_ptr cdt")
+
+
+class FFNBlockFn(torch.autograd.Function):
+    """y = LN(dropout(gelu(x W1^T + b1) W2^T + b2) + x)"""
+
+    @staticmethod
+    def forward(ctx, x32, x16, W1, b1, W2, b2, gamma, beta, W1_c, W2_c, cfg):
+        cdt = cfg.cdt
+        xc = _c(x32, x16, cdt)
+        M = xc.shape[0]
+        F = W1_c.shape[0]
+        z = torch.empty((M, F), device=xc.device, dtype=cdt)
+        h = ops.gemm(xc, W1_c, bias=b1, act=ops.ACT_GELU, aux_out=z, out_dtype=cdt)
+        pre = ops.gemm(h, W2_c, bias=b2, res=x32, out_dtype=torch.float32, drop_p=cfg.hid_p, drop_seed=cfg.seed,
+                       seed_ptr=cfg.seed_ptr)
+        y32, y16, mean, rstd = ops.layernorm_fwd(pre, gamma, beta, cfg.eps, True, _d16(cdt))
+        ctx.cfg = cfg
+        ctx.save_for_backward(xc, z, h, pre, mean, rstd, W1_c, W2_c, gamma)
+        if y16 is not None:
+            ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, _dy16):
+        cfg = ctx.cfg
+        xc, z, h, pre, mean, rstd, W1_c, W2_c, gamma = ctx.saved_tensors
+        cdt = cfg.cdt
+        dpre32, dpre_c, dgamma, dbeta, db2 = _ln_bwd_split(dy32.contiguous(), pre, gamma, mean, rstd, cdt, cfg.hid_p,
+                                                           cfg.seed, cfg.seed_ptr)
+        dW2 = ops.gemm(dpre_c, h, a_mn=True, b_mn=True, out_dtype=torch.float32)            # [H,F]
+        dz = ops.gemm(dpre_c, W2_c, b_mn=True, act=ops.ACT_DGELU, aux_in=z, out_dtype=cdt)   # [M,F]
+        db1 = ops.colsum(dz)
+        dW1 = ops.gemm(dz, xc, a_mn=True, b_mn=True, out_dtype=torch.float32)               # [F,H]
+        dx32 = ops.gemm(dz, W1_c, b_mn=True, res=dpre32, out_dtype=torch.float32)           # [M,H]
+        return dx32, None, dW1, db1, dW2, db2, dgamma, dbeta, None, None, None
+
+
+PanoCfg = namedtuple("PanoCfg", "B N heads eps hid_p seed seed_ptr cdt")
+
+
+class PanoLayerFn(torch.autograd.Function):
+    """pre-LN encoder layer:  y = x + drop(OutProj(Attn(LN1 x)));  out = y + drop(W2 drop(gelu(W1 LN2 y)))"""
+
+    @staticmethod
+    def forward(ctx, x32, kmask, Win, bin_, Wout, bout, W1, b1, W2, b2, g1, be1, g2, be2, Win_c, Wout_c, W1_c, W2_c, cfg):
+        cdt = cfg.cdt
+        H = x32.shape[1]
+        B, N = cfg.B, cfg.N
+        f32 = cdt == torch.float32
+        a32, a16, mean1, rstd1 = ops.layernorm_fwd(x32, g1, be1, cfg.eps, f32, _d16(cdt))
+        x2c = a32 if f32 else a16
+        qkv = ops.gemm(x2c, Win_c, bias=bin_, out_dtype=cdt)
+        q3 = qkv[:, :H].unflatten(0, (B, N))
+        k3 = qkv[:, H:2 * H].unflatten(0, (B, N))
+        v3 = qkv[:, 2 * H:].unflatten(0, (B, N))
+        o3, lse = ops.attn_fwd(q3, k3, v3, cfg.heads, kmask, None, 0.125, cfg.hid_p, cfg.seed, cfg.seed_ptr)
+        o2 = o3.view(B * N, H)
+        y32 = ops.gemm(o2, Wout_c, bias=bout, res=x32, out_dtype=torch.float32, drop_p=cfg.hid_p, drop_seed=cfg.seed + 1,
+                       seed_ptr=cfg.seed_ptr)
+        b32, b16, mean2, rstd2 = ops.layernorm_fwd(y32, g2, be2, cfg.eps, f32, _d16(cdt))
+        y2c = b32 if f32 else b16
+        F = W1_c.shape[0]
+        z = torch.empty((B * N, F), device=x32.device, dtype=cdt)
+        h = ops.gemm(y2c, W1_c, bias=b1, act=ops.ACT_GELU, aux_out=z, out_dtype=cdt, drop_p=cfg.hid_p,
+                     drop_seed=cfg.seed + 2, seed_ptr=cfg.seed_ptr)
+        out32 = ops.gemm(h, W2_c, bias=b2, res=y32, out_dtype=torch.float32, drop_p=cfg.hid_p, drop_seed=cfg.seed + 3,
+                         seed_ptr=cfg.seed_ptr)
+        ctx.cfg = cfg
+        ctx.save_for_backward(x32, x2c, qkv, o2, lse, y32, y2c, z, h, mean1, rstd1, mean2, rstd2, kmask, Win_c, Wout_c,
+                              W1_c, W2_c, g1, g2)
+        return out32
+
+    @staticmethod
+    def backward(ctx, dout32):
+        cfg = ctx.cfg
+        (x32, x2c, qkv, o2, lse, y32, y2c, z, h, mean1, rstd1, mean2, rstd2, kmask, Win_c, Wout_c, W1_c, W2_c, g1,
+         g2) = ctx.saved_tensors
+        cdt = cfg.cdt
+        H = x32.shape[1]
+        B, N = cfg.B, cfg.N
+        p, sp = cfg.hid_p, cfg.seed_ptr
+        dout32 = dout32.contiguous()
+        # FFN half
+        dout_c = ops.cast(dout32, cdt, drop_p=p, drop_seed=cfg.seed + 3, seed_ptr=sp) if (p > 0 or cdt != torch.float32) \
+            else dout32
+        db2 = ops.colsum(dout_c)
+        dW2 = ops.gemm(dout_c, h, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dz = ops.gemm(dout_c, W2_c, b_mn=True, act=ops.ACT_DGELU, aux_in=z, out_dtype=cdt, drop_p=p,
+                      drop_seed=cfg.seed + 2, seed_ptr=sp)
+        db1 = ops.colsum(dz)
+        dW1 = ops.gemm(dz, y2c, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dy2 = ops.gemm(dz, W1_c, b_mn=True, out_dtype=torch.float32)
+        dy32, _, dg2, dbe2, _ = ops.layernorm_bwd(dy2, y32, g2, mean2, rstd2, dout32, True, None)
+        # attention half
+        dy_c = ops.cast(dy32, cdt, drop_p=p, drop_seed=cfg.seed + 1, seed_ptr=sp) if (p > 0 or cdt != torch.float32) \
+            else dy32
+        dbout = ops.colsum(dy_c)
+        dWout = ops.gemm(dy_c, o2, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        do2 = ops.gemm(dy_c, Wout_c, b_mn=True, out_dtype=cdt)
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(do2.view(B, N, H), qkv[:, :H].unflatten(0, (B, N)), qkv[:, H:2 * H].unflatten(0, (B, N)),
+                     qkv[:, 2 * H:].unflatten(0, (B, N)), o2.view(B, N, H), lse, cfg.heads,
+                     dqkv[:, :H].unflatten(0, (B, N)), dqkv[:, H:2 * H].unflatten(0, (B, N)),
+                     dqkv[:, 2 * H:].unflatten(0, (B, N)), kmask, None, 0.125, p, cfg.seed, sp)
+        dbin = ops.colsum(dqkv)
+        dWin = ops.gemm(dqkv, x2c, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dx2 = ops.gemm(dqkv, Win_c, b_mn=True, out_dtype=torch.float32)
+        dx32, _, dg1, dbe1, _ = ops.layernorm_bwd(dx2, x32, g1, mean1, rstd1, dy32, True, None)
+        return (dx32, None, dWin, dbin, dWout, dbout, dW1, db1, dW2, db2, dg1, dbe1, dg2, dbe2, None, None, None, None,
+                None)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b), act in {none, relu, tanh, gelu}; fp32 in / fp32 out, GEMM in the compute dtype.
+    Shapes the tcgen05 path cannot take (K or N tiny: 7/14-wide position features, 1-wide heads) run on
+    the fp32 SIMT kernel regardless of the compute dtype."""
+
+    @staticmethod
+    def forward(ctx, x32, x16, W, b, W_c, act, cdt):
+        small = (W.shape[1] % 8 != 0) or W.shape[1] < 16 or W.shape[0] < 8
+        if small:
+            cdt = torch.float32
+            W_c = W
+        xc = _c(x32, x16, cdt)
+        aux = None
+        if act == ops.ACT_GELU:
+            aux = torch.empty((xc.shape[0], W.shape[0]), device=xc.device, dtype=cdt)
+        y = ops.gemm(xc, W_c, bias=b, act=act, aux_out=aux, out_dtype=torch.float32)
+        ctx.act, ctx.cdt = act, cdt
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(xc, W_c, y if act in (ops.ACT_RELU, ops.ACT_TANH) else None, aux)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, W_c, y, aux = ctx.saved_tensors
+        cdt = ctx.cdt
+        dy = dy.contiguous()
+        if ctx.act == ops.ACT_RELU:
+            dy = dy * (y > 0).to(dy.dtype)
+        elif ctx.act == ops.ACT_TANH:
+            dy = dy * (1.0 - y * y)
+        elif ctx.act == ops.ACT_GELU:
+            a = aux.float()
+            dy = dy * (0.5 * (1.0 + torch.erf(a * 0.7071067811865476)) + a * torch.exp(-0.5 * a * a) * 0.3989422804014327)
+        dyc = dy if cdt == torch.float32 else ops.cast(dy, cdt)
+        db = ops.colsum(dyc) if ctx.has_bias else None
+        dW = ops.gemm(dyc, xc, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dx = ops.gemm(dyc, W_c, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        return dx, None, dW, db, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """y = LN(x) with fp32 statistics; returns (y32, y16-or-None)."""
+
+    @staticmethod
+    def forward(ctx, x32, gamma, beta, eps, cdt):
+        y32, y16, mean, rstd = ops.layernorm_fwd(x32, gamma, beta, eps, True, _d16(cdt))
+        ctx.save_for_backward(x32, gamma, mean, rstd)
+        if y16 is not None:
+            ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy, _d16):
+        x32, gamma, mean, rstd = ctx.saved_tensors
+        dx32, _, dg, db, _ = ops.layernorm_bwd(dy.contiguous(), x32, gamma, mean, rstd, None, True, None)
+        return dx32, dg, db, None, None

@@ -41,7 +41,7 @@ def _rowmajor2d(t, name):
 
 
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_out=None, out=None, out_dtype=None,
-         out2=None, act=ACT_NONE, alpha=1.0, drop_p=0.0, drop_seed=0, force_simt=False):
+         out2=None, act=ACT_NONE, alpha=1.0, drop_p=0.0, drop_seed=0, seed_ptr=None, force_simt=False):
     """out[M,N] = epilogue(alpha * A B^T).  A: [M,K] (a_mn False) or [K,M] (a_mn True);
     B: [N,K] (b_mn False) or [K,N] (b_mn True).  See goat_gemm in include/goat_sm100.h."""
     _req_cuda(A, B, bias, res, aux_in, aux_out, out, out2)
@@ -80,6 +80,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
             raise ValueError("gemm: out2 must have the operand dtype and shape [M,N]")
         a.out2, a.ldc2 = out2.data_ptr(), _rowmajor2d(out2, "out2")
     a.act, a.alpha, a.drop_p, a.drop_seed = act, alpha, drop_p, drop_seed
+    a.drop_seed_ptr = None if seed_ptr is None else seed_ptr.data_ptr()
     a.force_simt = int(force_simt)
     _lib.check(_lib.lib().goat_gemm(C.byref(a), _stream()), "goat_gemm")
     return out
@@ -92,7 +93,7 @@ def _tok3(t, name, heads):
     return t.stride(1), t.stride(0)
 
 
-def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed):
+def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr=None):
     B, Nq, _ = q.shape
     Nk = k.shape[1]
     a = _lib.AttnArgs()
@@ -114,25 +115,26 @@ def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed):
     a.scale = scale
     a.lse = lse.data_ptr()
     a.drop_p, a.drop_seed = drop_p, drop_seed
+    a.drop_seed_ptr = None if seed_ptr is None else seed_ptr.data_ptr()
     return a
 
 
-def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0):
+def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0, seed_ptr=None):
     """-> (O [B,Nq,heads*64] same dtype, lse [B,heads,Nq] fp32)"""
     _req_cuda(q, k, v, kmask, bias)
     B, Nq, _ = q.shape
     o = torch.empty((B, Nq, heads * 64), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, heads, Nq), device=q.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed)
+    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr)
     _lib.check(_lib.lib().goat_attn_core_fwd(C.byref(a), _stream()), "goat_attn_core_fwd")
     return o, lse
 
 
 def attn_bwd(do, q, k, v, o, lse, heads, dq, dk, dv, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0,
-             want_dbias=False):
+             seed_ptr=None, want_dbias=False):
     """dq/dk/dv: preallocated views with the same strides as q/k/v.  -> dbias [B,Nq,Nk] fp32 or None"""
     _req_cuda(do, q, k, v, o, lse, dq, dk, dv)
-    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed)
+    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr)
     for name, t, ref in (("dq", dq, q), ("dk", dk, k), ("dv", dv, v), ("do", do, o)):
         if t.stride() != ref.stride() or t.shape != ref.shape or t.dtype != ref.dtype:
             raise ValueError("attn_bwd: %s must match the layout of its forward tensor" % name)
@@ -162,7 +164,7 @@ def layernorm_fwd(x, gamma, beta, eps, want32=True, dtype16=None):
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None, drop_p=0.0, drop_seed=0,
-                  want_colsum=False):
+                  seed_ptr=None, want_colsum=False):
     """-> (dx32 or None, dx16 or None, dgamma [H], dbeta [H], dcolsum [H] or None)"""
     _req_cuda(dy, x, gamma, mean, rstd, dres)
     M, H = x.shape
@@ -176,25 +178,28 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None
     dcol = torch.empty((H,), device=dev, dtype=torch.float32) if want_colsum else None
     ws = torch.empty((_lib.lib().goat_layernorm_bwd_workspace_bytes(M, H),), device=dev, dtype=torch.uint8)
     rc = _lib.lib().goat_layernorm_bwd(_p(dy), _p(x), dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
-                                       dt(dtype16) if dtype16 is not None else F16, drop_p, drop_seed, _p(dgamma),
-                                       _p(dbeta), _p(dcol), _p(ws), M, H, _stream())
+                                       dt(dtype16) if dtype16 is not None else F16, drop_p, drop_seed, _p(seed_ptr),
+                                       _p(dgamma), _p(dbeta), _p(dcol), _p(ws), M, H, _stream())
     _lib.check(rc, "goat_layernorm_bwd")
     return dx32, dx16, dgamma, dbeta, dcol
 
 
-def colsum(x):
+def colsum(x, out=None):
     """x [M,N] (unit inner stride) -> fp32 [N]"""
-    _req_cuda(x)
+    _req_cuda(x, out)
     ld = _rowmajor2d(x, "x")
     M, N = x.shape
-    out = torch.empty((N,), device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((N,), device=x.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or out.numel() != N or not out.is_contiguous():
+        raise ValueError("colsum: out must be contiguous fp32 [N]")
     ws = torch.empty((_lib.lib().goat_colsum_workspace_bytes(M, N),), device=x.device, dtype=torch.uint8)
     _lib.check(_lib.lib().goat_colsum(_p(x), dt(x), M, N, ld, _p(out), _p(ws), _stream()), "goat_colsum")
     return out
 
 
-def cast(src, dtype, out=None):
-    """contiguous tensor -> new tensor (or `out`) of `dtype`"""
+def cast(src, dtype, out=None, drop_p=0.0, drop_seed=0, seed_ptr=None):
+    """contiguous tensor -> new tensor (or `out`) of `dtype`; optional dropout mask by linear element index"""
     _req_cuda(src, out)
     if not src.is_contiguous():
         raise ValueError("cast: src must be contiguous")
@@ -202,5 +207,6 @@ def cast(src, dtype, out=None):
         out = torch.empty(src.shape, device=src.device, dtype=dtype)
     elif not out.is_contiguous() or out.numel() != src.numel():
         raise ValueError("cast: bad out")
-    _lib.check(_lib.lib().goat_cast(_p(src), dt(src), _p(out), dt(out), src.numel(), _stream()), "goat_cast")
+    _lib.check(_lib.lib().goat_dropout_cast(_p(src), dt(src), _p(out), dt(out), src.numel(), drop_p, drop_seed,
+                                            _p(seed_ptr), _stream()), "goat_dropout_cast")
     return out
