@@ -164,6 +164,26 @@ int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
 int goat_dropout_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float drop_p,
                       uint64_t drop_seed, const uint64_t* drop_seed_ptr, goat_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused optimizer step over ONE flat fp32 parameter buffer (the caller lays the model's parameters out
+ * back to back; weight-decayed tensors first).  Replaces torch.nn.utils.clip_grad_norm_ +
+ * the per-tensor AdamW loop (P/train_r2r_goat.py:349-366, P/optim/adamw.py:53-110; decay groups
+ * P/optim/misc.py:12-22).
+ *   goat_sumsq: partial[i] = sum of squares of a slice of g; *nparts_out (HOST int) = number of slices.
+ *               partial needs goat_sumsq_workspace_bytes() bytes.
+ *   goat_adamw_step: norm = sqrt(sum partial) * hp[8]; coef = hp[8] * min(1, hp[7] / (norm + 1e-6));
+ *               g' = coef*g; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2;
+ *               p -= lr * sqrt(bc2)/bc1 * m / (sqrt(v) + eps); p -= lr*wd*p for the first n_decay elements;
+ *               shadow (optional, F16/BF16) = p rounded -- the operand copy the tcgen05 GEMMs read.
+ *               hp is a DEVICE array of 9 floats {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t,
+ *               max_grad_norm (<=0: off), grad pre-scale}; norm_out (optional, device) receives the norm.
+ * ------------------------------------------------------------------------------------------ */
+size_t goat_sumsq_workspace_bytes(void);
+int goat_sumsq(const float* g, long long n, float* partial, int* nparts_out, goat_stream_t stream);
+int goat_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
+                    long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
+                    goat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -413,3 +413,38 @@ def c2_shapes():
     for i in range(3):
         d.update(cross_layer_shapes("local_encoder.encoder.crossattention.%d." % i))
     return d
+
+
+# --------------------------------------------------------------------------------------
+# optimizer step (for the CPU baseline of a full training step and the fused-AdamW parity test)
+# --------------------------------------------------------------------------------------
+def clip_grad_norm(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ semantics (P/train_r2r_goat.py:352): total L2 norm over all grads,
+    scale by max_norm / (norm + 1e-6) when that is < 1.  Returns (norm, coefficient)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = max_norm / (total + 1e-6)
+    coef = torch.clamp(coef, max=1.0)
+    return total, coef
+
+
+def adamw_step(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
+    """One AdamW update of a single tensor, in place.  P/optim/adamw.py:85-110:
+    m,v EMAs; denom = sqrt(v) + eps; step_size = lr * sqrt(1-b2^t) / (1-b1^t); p -= step_size * m/denom;
+    then decoupled decay p -= lr * wd * p."""
+    b1, b2 = betas
+    m.mul_(b1).add_(g, alpha=1.0 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+    denom = v.sqrt().add_(eps)
+    step_size = lr
+    if correct_bias:
+        step_size = step_size * math.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
+    p.addcdiv_(m, denom, value=-step_size)
+    if weight_decay > 0.0:
+        p.add_(p, alpha=-lr * weight_decay)
+    return p
+
+
+def c2_loss(txt_out, vp_out):
+    """The synthetic training objective bench.py / smoke() put on the C2 workload: mean square of both
+    output streams (any differentiable scalar exercises the same forward + backward kernels)."""
+    return 0.5 * (txt_out.float() ** 2).mean() + 0.5 * (vp_out.float() ** 2).mean()

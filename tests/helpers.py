@@ -21,7 +21,7 @@ def digest(t):
                          t[0].item(), t[-1].item()], dtype=torch.float64)
 
 
-def assert_digests(gold, grads, rtol, prefix="gdig.", atol=1e-4):
+def assert_digests(gold, grads, rtol, prefix="gdig.", atol=1e-4, key_bias_atol=None):
     """grads: {param name: grad tensor}.  Compares against the 5-number digests stored in a fixture.
     The tolerance is relative to the abs-sum (digest[1]), the natural scale of the cancelling sums,
     plus an absolute floor: key-bias grads are analytically zero (softmax is shift-invariant), so the
@@ -36,6 +36,11 @@ def assert_digests(gold, grads, rtol, prefix="gdig.", atol=1e-4):
         ref = v.double()
         scale = ref[1].abs().item() + 1e-30
         err = (d - ref).abs()
+        if key_bias_atol is not None and name.endswith("key.bias"):
+            # analytically zero: only rounding noise on both sides (16-bit operands make it ~1e-3 per element)
+            assert d[1].item() <= key_bias_atol, (name, "abssum of an analytically-zero grad", d)
+            n += 1
+            continue
         # sum / cos-sum are cancelling sums over numel terms: allow rtol * abs-sum
         assert err[0].item() <= rtol * scale + atol, (name, "sum", d, ref)
         assert err[1].item() <= rtol * scale + atol, (name, "abssum", d, ref)

@@ -1,0 +1,174 @@
+"""GPU parity: the drop-in blocks (vln_goat_b200.modules -> C ABI -> sm_100a kernels) against the golden
+fixtures produced by the unmodified reference (tests/golden/make_golden.py) and against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): 1e-5 in fp32 mode, 1e-3 in fp16 mode, both relative to the
+output scale max(1, max|ref|); bf16 operands carry 8x the fp16 rounding step, so bf16 is held to 8e-3.
+Parameter gradients are compared through the 5-number digests stored in the fixtures.
+"""
+import pytest
+import torch
+
+from oracle import goat_oracle as O
+from tests.helpers import assert_digests, golden, maxerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.float16: 1e-3, torch.bfloat16: 8e-3}
+DIG = {torch.float32: 2e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}
+KB = {torch.float32: None, torch.float16: 2.0, torch.bfloat16: 16.0}   # abs-sum bound over 768 noise-only elements
+DTYPES = [torch.float32, torch.float16, torch.bfloat16]
+
+
+def _rel(got, ref):
+    return maxerr(got, ref) / max(1.0, ref.abs().max().item())
+
+
+def _cuda_leaf(t):
+    return t.float().cuda().requires_grad_(True)
+
+
+def _load(module, params):
+    missing, unexpected = module.load_state_dict(params, strict=False)
+    assert not unexpected, unexpected
+    return module.cuda().eval()
+
+
+def _grads(module):
+    return {k: v.grad for k, v in module.named_parameters() if v.grad is not None}
+
+
+@pytest.fixture(autouse=True)
+def _lib_loaded():
+    from vln_goat_b200 import _lib
+    assert _lib.lib().goat_device_supported() == 1, "needs an sm_100 device"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_c1_cross_layer(dtype):
+    """BASELINE.json configs[0]: one BertCrossLayer, pano [2,36,768] x text [2,80,768], lengths {80,57}."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    g = golden("c1_cross_layer")
+    layer = _load(M.BertCrossLayer(GoatConfig()), O.seeded_params(O.cross_layer_shapes(), seed=1))
+    q, kv = _cuda_leaf(g["q"]), _cuda_leaf(g["kv"])
+    kvm = M.extend_neg_masks(M.gen_seq_masks(g["txt_lens"].cuda(), 80))
+    qm = torch.zeros(2, 1, 1, 36, device="cuda")
+    with runtime.compute(dtype):
+        out = layer(q, kv, attention_mask=qm, encoder_attention_mask=kvm)[0]
+        (out * g["w_out"].cuda()).sum().backward()
+        att = layer.crossattention(g["q"].cuda(), None, None, g["kv"].cuda(), kvm)[0]
+    assert _rel(out, g["out"]) < TOL[dtype]
+    assert _rel(att, g["cross_attn_out"]) < TOL[dtype]
+    assert _rel(q.grad, g["dq"]) < TOL[dtype]
+    assert _rel(kv.grad, g["dkv"]) < TOL[dtype]
+    grads = _grads(layer)
+    assert_digests({k: v for k, v in g.items() if "lang_" not in k}, grads, rtol=DIG[dtype], key_bias_atol=KB[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_xenc_sprels(dtype):
+    """CrossmodalEncoder(3) with the graph_sprels bias and ragged lengths; d(sprels) flows back."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    g = golden("xenc_sprels")
+    shapes = {}
+    for i in range(3):
+        shapes.update(O.cross_layer_shapes("crossattention.%d." % i))
+    enc = _load(M.CrossmodalEncoder(GoatConfig()), O.seeded_params(shapes, seed=2))
+    gm, tx, sp = _cuda_leaf(g["gmap"]), _cuda_leaf(g["txt"]), _cuda_leaf(g["sprels"])
+    with runtime.compute(dtype):
+        out = enc(gm, M.gen_seq_masks(g["gmap_lens"].cuda(), 12), tx, M.gen_seq_masks(g["txt_lens"].cuda(), 40),
+                  graph_sprels=sp)
+        (out * g["w_out"].cuda()).sum().backward()
+    assert _rel(out, g["out"]) < TOL[dtype]
+    assert _rel(gm.grad, g["dgmap"]) < TOL[dtype]
+    assert _rel(tx.grad, g["dtxt"]) < TOL[dtype]
+    assert _rel(sp.grad, g["dsprels"]) < TOL[dtype]
+    assert_digests({k: v for k, v in g.items() if "lang_" not in k}, _grads(enc), rtol=DIG[dtype], key_bias_atol=KB[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_lang_encoder(dtype):
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    g = golden("lang_encoder")
+    shapes = {}
+    for i in range(6):
+        shapes.update(O.roberta_layer_shapes("layer.%d." % i))
+    le = _load(M.LanguageEncoder(GoatConfig()), O.seeded_params(shapes, seed=3))
+    x = _cuda_leaf(g["x"])
+    with runtime.compute(dtype):
+        out = le(x, M.gen_seq_masks(g["txt_lens"].cuda(), 80))
+        (out * g["w_out"].cuda()).sum().backward()
+    assert _rel(out, g["out"]) < 2 * TOL[dtype]
+    assert _rel(x.grad, g["dx"]) < 2 * TOL[dtype]
+    assert_digests(g, _grads(le), rtol=DIG[dtype], key_bias_atol=KB[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pano_encoder(dtype):
+    """2 pre-LN layers + final LN, -inf key padding {36, 29}."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    g = golden("pano_encoder")
+    pe = _load(M.create_transformer_encoder(GoatConfig(), 2, norm=True), O.seeded_params(O.pano_encoder_shapes(), seed=4))
+    x = _cuda_leaf(g["x"])
+    with runtime.compute(dtype):
+        out = pe(x, src_key_padding_mask=M.gen_seq_masks(g["view_lens"].cuda(), 36).logical_not())
+        (out * g["w_out"].cuda()).sum().backward()
+    assert _rel(out, g["out"]) < TOL[dtype]
+    assert _rel(x.grad, g["dx"]) < 2 * TOL[dtype]
+    assert_digests(g, _grads(pe), rtol=DIG[dtype], key_bias_atol=KB[dtype])
+
+
+def test_state_dict_keys_match_reference_fixture():
+    """Every parameter name the reference BertCrossLayer / pano encoder owns exists here with the same shape."""
+    from vln_goat_b200 import modules as M
+    from vln_goat_b200.config import GoatConfig
+    layer = M.BertCrossLayer(GoatConfig())
+    sd = layer.state_dict()
+    for k, shp in O.cross_layer_shapes().items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    pe = M.create_transformer_encoder(GoatConfig(), 2, norm=True)
+    sd = pe.state_dict()
+    for k, shp in O.pano_encoder_shapes().items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+
+
+@pytest.mark.parametrize("B,Nq,Nk", [(1, 1, 1), (2, 3, 24), (2, 37, 80), (3, 38, 35), (2, 60, 200), (1, 128, 512),
+                                     (16, 37, 50), (2, 38, 39)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_attention_block_shape_sweep(B, Nq, Nk, dtype):
+    """BertAttention (cross) vs the CPU oracle over the shape sweep of SURVEY.md Appendix B.4, ragged key lengths."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    P = O.seeded_params(O.attn_shapes(""), seed=11)
+    att = _load(M.BertAttention(GoatConfig()), P)
+    g = torch.Generator().manual_seed(B * 1000 + Nq * 10 + Nk)
+    x = torch.randn(B, Nq, 768, generator=g)
+    enc = torch.randn(B, Nk, 768, generator=g)
+    lens = torch.randint(1, Nk + 1, (B,), generator=g)
+    lens[0] = Nk
+    km = O.extend_neg_masks(O.gen_seq_masks(lens, Nk))
+    w = torch.randn(B, Nq, 768, generator=g)
+    xr, er = x.clone().requires_grad_(True), enc.clone().requires_grad_(True)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    ref = O.bert_attention(Pr, "", xr, None, er, km)
+    (ref * w).sum().backward()
+    xc, ec = _cuda_leaf(x), _cuda_leaf(enc)
+    with runtime.compute(dtype):
+        out = att(xc, None, None, ec, km.cuda())[0]
+        (out * w.cuda()).sum().backward()
+    assert _rel(out, ref.detach()) < TOL[dtype]
+    assert _rel(xc.grad, xr.grad) < TOL[dtype]
+    assert _rel(ec.grad, er.grad) < TOL[dtype]
+    for k, v in att.named_parameters():
+        assert _rel(v.grad, Pr[k].grad) < 4 * TOL[dtype], k
+
+
+def test_no_cpu_fallback():
+    from vln_goat_b200 import modules as M
+    from vln_goat_b200.config import GoatConfig
+    att = M.BertAttention(GoatConfig())
+    with pytest.raises(RuntimeError):
+        att(torch.randn(1, 4, 768))

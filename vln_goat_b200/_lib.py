@@ -67,6 +67,10 @@ SYMBOLS = {
     "goat_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "goat_dropout_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint64,
                                     C.c_void_p, C.c_void_p]),
+    "goat_sumsq_workspace_bytes": (C.c_size_t, []),
+    "goat_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
+    "goat_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong,
+                                  C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

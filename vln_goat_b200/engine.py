@@ -1,0 +1,223 @@
+"""Training-step plumbing around the kernels: flat parameter storage, fused optimizer, CUDA-graph replay.
+
+What the reference does per optimizer step (P/train_r2r_goat.py:301-366) and what replaces it here:
+
+  reference                                                     here
+  ------------------------------------------------------------  ------------------------------------------------
+  ~600 separate parameter tensors, fp32                         FlatParams: ONE fp32 buffer (params are views), one
+                                                                fp32 gradient buffer, one 16-bit operand shadow;
+                                                                q/k/v weights of each attention sit back to back so
+                                                                the fused-QKV GEMM reads them with no concat
+  autograd accumulates every weight grad into p.grad            wgrad GEMMs / LN-backward write straight into the flat
+                                                                gradient views (functional.py ``_goat_grad``)
+  DDP bucketed all-reduce (P/utils/misc.py:52-58)               one NCCL all-reduce (sum) over the flat buffer; the
+                                                                1/world average is folded into the optimizer kernel
+  clip_grad_norm_ + per-tensor AdamW loop (P/optim/adamw.py)    goat_sumsq + goat_adamw_step (2 launches)
+  ~500 eager launches per fwd+bwd                               the whole fwd+bwd is captured once in a CUDA graph
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, functional as Fn, ops
+
+NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")  # P/optim/misc.py:13
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class FlatParams(object):
+    """Re-homes every trainable parameter of ``model`` (already on its CUDA device) into one flat fp32 buffer.
+
+    Layout: [weight-decayed tensors | no-decay tensors], each padded to 8 elements (16-byte aligned fp32 and
+    16-bit views).  ``named_parameters`` order is kept inside each group, which puts query/key/value weights
+    (and, in the other group, their biases) back to back.
+    """
+
+    def __init__(self, model, shadow_dtype=None, no_decay=NO_DECAY, only=None):
+        """``only``: optional collection of parameters to flatten (see ``active_parameters``); the rest of the
+        model is left untouched and never updated -- the reference's AdamW likewise skips parameters whose
+        ``grad`` is None (P/optim/adamw.py:66-67), which DDP's find_unused_parameters=True relies on."""
+        named = []
+        seen = set()
+        keep = None if only is None else set(id(p) for p in only)
+        for n, p in model.named_parameters():
+            if p.requires_grad and id(p) not in seen and (keep is None or id(p) in keep):
+                seen.add(id(p))
+                named.append((n, p))
+        if not named:
+            raise ValueError("model has no trainable parameters")
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatParams needs the model on a CUDA device (no CPU path)")
+        decay = [(n, p) for n, p in named if not any(nd in n for nd in no_decay)]
+        nodecay = [(n, p) for n, p in named if any(nd in n for nd in no_decay)]
+        self.names, self.params, self.offsets = [], [], []
+        off = 0
+        for n, p in decay + nodecay:
+            self.names.append(n)
+            self.params.append(p)
+            self.offsets.append(off)
+            off += _pad8(p.numel())
+            if len(self.params) == len(decay):
+                self.n_decay = off
+        if not decay:
+            self.n_decay = 0
+        self.numel = off
+        self.p = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.shadow_dtype = shadow_dtype if shadow_dtype in (torch.float16, torch.bfloat16) else None
+        self.shadow = torch.zeros(off, device=dev, dtype=self.shadow_dtype) if self.shadow_dtype else None
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.p[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = self.p[o:o + n].view(p.shape)
+            p.grad = None
+            p._goat_grad = self.g[o:o + n].view(p.shape)
+            p._goat_fresh = True
+            if self.shadow is not None:
+                p._goat_shadow = self.shadow[o:o + n].view(p.shape)
+        self.refresh_shadow()
+        ws = _lib.lib().goat_sumsq_workspace_bytes()
+        self._partial = torch.zeros(ws // 4, device=dev, dtype=torch.float32)
+        self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._hp = torch.zeros(9, device=dev, dtype=torch.float32)
+        self.step_count = 0
+
+    def refresh_shadow(self):
+        """Re-derive the 16-bit operand copies from the fp32 masters (after load_state_dict etc.)."""
+        if self.shadow is not None:
+            ops.cast(self.p, self.shadow_dtype, out=self.shadow)
+
+    def begin_step(self):
+        """Mark every gradient view as unwritten: the first backward write of the step overwrites, later ones
+        (a parameter used twice) accumulate.  No memset of the gradient buffer is needed."""
+        for p in self.params:
+            p._goat_fresh = True
+
+    def unwritten(self):
+        return [n for n, p in zip(self.names, self.params) if p._goat_fresh]
+
+    def grads_to_autograd(self):
+        """Expose the flat gradient views as ``param.grad`` (for code that inspects grads the torch way)."""
+        for p in self.params:
+            p.grad = p._goat_grad
+
+    def all_reduce(self, group=None):
+        """Sum the flat gradient over ranks (the average is applied by the optimizer kernel's pre-scale)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, grad_scale=1.0,
+                   correct_bias=True):
+        """clip_grad_norm_(max_grad_norm) + AdamW (P/optim/adamw.py:85-110 numerics) on the flat buffer."""
+        self.step_count += 1
+        t = self.step_count
+        # pageable source on purpose: the runtime stages a small pageable H2D copy before returning, so the
+        # host tensor can be dropped / rebuilt next step without racing the DMA (a reused pinned buffer could)
+        h = torch.tensor([lr, betas[0], betas[1], eps, weight_decay,
+                          (1.0 - betas[0] ** t) if correct_bias else 1.0,
+                          (1.0 - betas[1] ** t) if correct_bias else 1.0, max_grad_norm, grad_scale], dtype=torch.float32)
+        self._hp.copy_(h, non_blocking=True)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nparts = C.c_int(0)
+        L = _lib.lib()
+        _lib.check(L.goat_sumsq(self.g.data_ptr(), self.numel, self._partial.data_ptr(), C.byref(nparts), st), "goat_sumsq")
+        sd = ops.dt(self.shadow_dtype) if self.shadow is not None else 0
+        _lib.check(L.goat_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                     self.shadow.data_ptr() if self.shadow is not None else None, sd, self.numel,
+                                     self.n_decay, self._hp.data_ptr(), self._partial.data_ptr(), nparts.value,
+                                     self.grad_norm.data_ptr(), st), "goat_adamw_step")
+        ops.LAUNCHES[0] += 2
+
+
+def active_parameters(model, loss_fn, inputs):
+    """One eager forward+backward through plain autograd; returns the parameters that received a gradient
+    (the set a given task / mode actually trains -- e.g. the pretrain-only ``lang_*`` blocks of BertCrossLayer,
+    P/model/Bert_backbone.py:673-676, take no part in the SAP / CFP / navigation forward)."""
+    for p in model.parameters():
+        p.grad = None
+    loss = loss_fn(*inputs)
+    loss.backward()
+    torch.cuda.synchronize()
+    act = [p for p in model.parameters() if p.grad is not None]
+    for p in model.parameters():
+        p.grad = None
+    return act
+
+
+def warmup_linear(step, warmup_step, tot_step):
+    """BERT schedule, P/optim/sched.py:17-21"""
+    if step < warmup_step:
+        return step / warmup_step
+    return max(0, (tot_step - step) / (tot_step - warmup_step))
+
+
+class TrainStep(object):
+    """One optimizer step = forward + backward (captured in a CUDA graph) + gradient all-reduce + fused AdamW.
+
+    ``loss_fn(*static_inputs) -> scalar loss tensor`` must be shape-static; call ``step(*new_inputs)`` with
+    tensors of the same shapes (device or pinned-host; they are copied into the captured input buffers).
+    """
+
+    def __init__(self, flat, loss_fn, example_inputs, lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01,
+                 max_grad_norm=5.0, use_graph=True, warmup_iters=2):
+        self.flat, self.loss_fn = flat, loss_fn
+        self.opt = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        self.static_inputs = [t.clone() if t.is_cuda else t.cuda() for t in example_inputs]
+        dev = self.static_inputs[0].device
+        self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
+        Fn.set_seed_ptr(self.seed)
+        self.loss = None
+        self.graph = None
+        self.launches_per_step = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup_iters):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        missing = flat.unwritten()
+        if missing:
+            raise RuntimeError("parameters without a gradient in the captured step (stale flat grads): %s" % missing[:8])
+        n0 = ops.LAUNCHES[0]
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._fwd_bwd()
+        else:
+            self._fwd_bwd()
+        self.launches_per_step = ops.LAUNCHES[0] - n0 + 2  # + sumsq + adamw
+
+    def _fwd_bwd(self):
+        self.flat.begin_step()
+        loss = self.loss_fn(*self.static_inputs)
+        loss.backward()
+        self.seed.add_(1)
+        self.loss = loss.detach()
+
+    def load_inputs(self, inputs):
+        for dst, src in zip(self.static_inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+
+    def step(self, inputs=None):
+        if inputs is not None:
+            self.load_inputs(inputs)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._fwd_bwd()
+        world = self.flat.all_reduce()
+        self.flat.adamw_step(grad_scale=1.0 / world, **self.opt)
+        return self.loss
+
+
+__all__ = ["FlatParams", "TrainStep", "active_parameters", "warmup_linear", "NO_DECAY"]

@@ -22,6 +22,22 @@ from . import ops
 _seed_counter = itertools.count(1)
 
 
+_seed_ptr = None
+
+
+def seed_ptr():
+    """Optional device word (uint64 as int64 tensor [1]) every dropout kernel adds to its seed: bump it between
+    CUDA-graph replays so a captured step draws fresh masks (engine.TrainStep does)."""
+    return _seed_ptr
+
+
+def set_seed_ptr(t):
+    global _seed_ptr
+    if t is not None and (t.dtype != torch.int64 or t.numel() != 1 or not t.is_cuda):
+        raise ValueError("seed_ptr must be a CUDA int64 tensor with one element")
+    _seed_ptr = t
+
+
 def next_seed():
     """A fresh host-side dropout seed (kernels add the optional device-side step counter to it)."""
     return (next(_seed_counter) * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF
@@ -40,13 +56,97 @@ def _d16(cdt):
     return None if cdt == torch.float32 else cdt
 
 
-def _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, p, seed, seed_ptr):
+def _split_rows(t, params):
+    out, r = [], 0
+    for p in params:
+        out.append(t[r:r + p.shape[0]])
+        r += p.shape[0]
+    return tuple(out)
+
+
+def _grad_into(params, fn, can_acc):
+    """Produce the gradient of one parameter, or of several whose rows are concatenated (fused QKV).
+
+    ``fn(out, acc)`` computes it into ``out`` (allocating when None), adding to the existing contents when
+    ``acc``.  If the parameters live in an engine.FlatParams buffer the result is written straight into their
+    flat gradient views (first write of a step overwrites, later writes accumulate) and None is returned for
+    autograd; otherwise the tensors are returned for autograd to accumulate the usual way."""
+    dsts = [getattr(p, "_goat_grad", None) for p in params]
+    if all(d is not None for d in dsts):
+        from . import runtime
+        fresh = [p._goat_fresh for p in params]
+        if len(dsts) == 1 or runtime._adjacent(dsts):
+            dst = dsts[0] if len(dsts) == 1 else runtime._fused_view(dsts)
+            if all(fresh):
+                fn(dst, False)
+            elif not any(fresh) and can_acc:
+                fn(dst, True)
+            else:
+                t = fn(None, False)
+                for d, part, f in zip(dsts, _split_rows(t, params), fresh):
+                    d.copy_(part) if f else d.add_(part)
+        else:
+            t = fn(None, False)
+            for d, part, f in zip(dsts, _split_rows(t, params), fresh):
+                d.copy_(part) if f else d.add_(part)
+        for p in params:
+            p._goat_fresh = False
+        return (None,) * len(params)
+    t = fn(None, False)
+    return _split_rows(t, params) if len(params) > 1 else (t,)
+
+
+def _wgrad(params, dy_c, x_c):
+    """dW = dY^T X for weight(s) [N,K] (rows of several weights concatenated)."""
+    def fn(out, acc):
+        return ops.gemm(dy_c, x_c, a_mn=True, b_mn=True, out=out, res=out if acc else None, out_dtype=torch.float32)
+    return _grad_into(params, fn, True)
+
+
+def _bgrad(params, dy_c):
+    """db = column sums of dY."""
+    if params[0] is None:
+        return (None,) * len(params)
+    return _grad_into(params, lambda out, acc: ops.colsum(dy_c, out=out), False)
+
+
+def _vgrad(param, t):
+    """a gradient vector that a kernel already produced (LayerNorm dgamma/dbeta, LN-fused bias column sums)"""
+    if param is None:
+        return None
+    return _grad_into((param,), lambda out, acc: t if out is None else out.copy_(t), False)[0]
+
+
+def _vdst(param):
+    """flat-gradient destination for a vector gradient if it can simply be overwritten this step, else None"""
+    if param is None:
+        return None
+    d = getattr(param, "_goat_grad", None)
+    if d is None or not param._goat_fresh or not d.is_contiguous():
+        return None
+    param._goat_fresh = False
+    return d
+
+
+def _ln_bwd(dy32, x, gamma, mean, rstd, dres, cdt16, p, seed, seed_ptr, gamma_p, beta_p, bias_p=None):
+    """LayerNorm backward with dgamma / dbeta (/ the producing Linear's bias grad) landing in the flat gradient
+    buffer when there is one.  -> (dx32, dx16-or-None, dgamma, dbeta, dbias) with None for in-place grads."""
+    og, ob = _vdst(gamma_p), _vdst(beta_p)
+    oc = _vdst(bias_p)
+    dx32, dx16, dg, db, dcol = ops.layernorm_bwd(dy32, x, gamma, mean, rstd, dres, True, cdt16, p, seed, seed_ptr,
+                                                 want_colsum=bias_p is not None, dgamma_out=og, dbeta_out=ob,
+                                                 dcol_out=oc)
+    return (dx32, dx16, None if og is not None else _vgrad(gamma_p, dg), None if ob is not None else _vgrad(beta_p, db),
+            None if (oc is not None or bias_p is None) else _vgrad(bias_p, dcol))
+
+
+def _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, p, seed, seed_ptr, gamma_p, beta_p, bias_p):
     """LN backward of a post-LN block: (residual-path grad fp32, GEMM-operand grad in the compute dtype with the
     hidden-dropout mask applied, dgamma, dbeta, bias grad of the producing Linear)."""
     if cdt == torch.float32 and p == 0.0:
-        d32, _, dg, db, dcol = ops.layernorm_bwd(dy32, pre, gamma, mean, rstd, None, True, None, want_colsum=True)
+        d32, _, dg, db, dcol = _ln_bwd(dy32, pre, gamma, mean, rstd, None, None, 0.0, 0, None, gamma_p, beta_p, bias_p)
         return d32, d32, dg, db, dcol
-    return ops.layernorm_bwd(dy32, pre, gamma, mean, rstd, None, True, cdt, p, seed, seed_ptr, want_colsum=True)
+    return _ln_bwd(dy32, pre, gamma, mean, rstd, None, cdt, p, seed, seed_ptr, gamma_p, beta_p, bias_p)
 
 
 AttnCfg = namedtuple("AttnCfg", "B Nq Nk heads eps attn_p hid_p seed seed_ptr cross cdt")
@@ -83,6 +183,7 @@ class AttnBlockFn(torch.autograd.Function):
                        seed_ptr=cfg.seed_ptr)
         y32, y16, mean, rstd = ops.layernorm_fwd(pre, gamma, beta, cfg.eps, True, _d16(cdt))
         ctx.cfg = cfg
+        ctx.params = (Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta)
         ctx.save_for_backward(xc, kvc, qkv, kvp, o2, lse, pre, mean, rstd, kmask, bias, Wqkv_c, Wo_c, gamma)
         if y16 is not None:
             ctx.mark_non_differentiable(y16)
@@ -92,14 +193,15 @@ class AttnBlockFn(torch.autograd.Function):
     def backward(ctx, dy32, _dy16):
         cfg = ctx.cfg
         xc, kvc, qkv, kvp, o2, lse, pre, mean, rstd, kmask, bias, Wqkv_c, Wo_c, gamma = ctx.saved_tensors
+        Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma_p, beta_p = ctx.params
         cdt = cfg.cdt
         H = pre.shape[1]
         B, Nq, Nk = cfg.B, cfg.Nq, cfg.Nk
         dy32 = dy32.contiguous()
         # LN backward: dpre32 feeds the residual path, dpre_c (dropout-masked) feeds the out-proj GEMMs
         dpre32, dpre_c, dgamma, dbeta, dbo = _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, cfg.hid_p, cfg.seed + 1,
-                                                           cfg.seed_ptr)
-        dWo = ops.gemm(dpre_c, o2, a_mn=True, b_mn=True, out_dtype=torch.float32)          # [H,H]
+                                                           cfg.seed_ptr, gamma_p, beta_p, bo)
+        dWo, = _wgrad((Wo,), dpre_c, o2)                                                    # [H,H]
         do2 = ops.gemm(dpre_c, Wo_c, b_mn=True, out_dtype=cdt)                              # [M,H]
         want_dbias = bias is not None and ctx.needs_input_grad[5]
         if not cfg.cross:
@@ -117,20 +219,18 @@ class AttnBlockFn(torch.autograd.Function):
                              kmask, bias, 0.125, cfg.attn_p, cfg.seed, cfg.seed_ptr, want_dbias=want_dbias)
         dkv32 = None
         if not cfg.cross:
-            dW = ops.gemm(dqkv, xc, a_mn=True, b_mn=True, out_dtype=torch.float32)          # [3H,H]
-            db = ops.colsum(dqkv)
+            dWq, dWk, dWv = _wgrad((Wq, Wk, Wv), dqkv, xc)                                   # [3H,H]
+            dbq, dbk, dbv = _bgrad((bq, bk, bv), dqkv)
             dx32 = ops.gemm(dqkv, Wqkv_c, b_mn=True, res=dpre32, out_dtype=torch.float32)   # [M,H]
         else:
-            dW = torch.empty((3 * H, H), device=xc.device, dtype=torch.float32)
-            db = torch.empty((3 * H,), device=xc.device, dtype=torch.float32)
-            ops.gemm(dqkv, xc, a_mn=True, b_mn=True, out=dW[:H])                             # dWq  [H,H]
-            ops.gemm(dkvp, kvc, a_mn=True, b_mn=True, out=dW[H:])                            # dWkv [2H,H]
-            ops.colsum(dqkv, out=db[:H])
-            ops.colsum(dkvp, out=db[H:])
+            dWq, = _wgrad((Wq,), dqkv, xc)                                                   # [H,H]
+            dWk, dWv = _wgrad((Wk, Wv), dkvp, kvc)                                           # [2H,H]
+            dbq, = _bgrad((bq,), dqkv)
+            dbk, dbv = _bgrad((bk, bv), dkvp)
             dx32 = ops.gemm(dqkv, Wqkv_c[:H], b_mn=True, res=dpre32, out_dtype=torch.float32)
             if ctx.needs_input_grad[2]:
                 dkv32 = ops.gemm(dkvp, Wqkv_c[H:], b_mn=True, out_dtype=torch.float32)      # [Mk,H]
-        return (dx32, None, dkv32, None, None, dbias, dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:],
+        return (dx32, None, dkv32, None, None, dbias, dWq, dbq, dWk, dbk, dWv, dbv,
                 dWo, dbo, dgamma, dbeta, None, None, None, None)
 
 
@@ -152,6 +252,7 @@ class FFNBlockFn(torch.autograd.Function):
                        seed_ptr=cfg.seed_ptr)
         y32, y16, mean, rstd = ops.layernorm_fwd(pre, gamma, beta, cfg.eps, True, _d16(cdt))
         ctx.cfg = cfg
+        ctx.params = (W1, b1, W2, b2, gamma, beta)
         ctx.save_for_backward(xc, z, h, pre, mean, rstd, W1_c, W2_c, gamma)
         if y16 is not None:
             ctx.mark_non_differentiable(y16)
@@ -162,12 +263,13 @@ class FFNBlockFn(torch.autograd.Function):
         cfg = ctx.cfg
         xc, z, h, pre, mean, rstd, W1_c, W2_c, gamma = ctx.saved_tensors
         cdt = cfg.cdt
+        W1, b1, W2, b2, gamma_p, beta_p = ctx.params
         dpre32, dpre_c, dgamma, dbeta, db2 = _ln_bwd_split(dy32.contiguous(), pre, gamma, mean, rstd, cdt, cfg.hid_p,
-                                                           cfg.seed, cfg.seed_ptr)
-        dW2 = ops.gemm(dpre_c, h, a_mn=True, b_mn=True, out_dtype=torch.float32)            # [H,F]
+                                                           cfg.seed, cfg.seed_ptr, gamma_p, beta_p, b2)
+        dW2, = _wgrad((W2,), dpre_c, h)                                                      # [H,F]
         dz = ops.gemm(dpre_c, W2_c, b_mn=True, act=ops.ACT_DGELU, aux_in=z, out_dtype=cdt)   # [M,F]
-        db1 = ops.colsum(dz)
-        dW1 = ops.gemm(dz, xc, a_mn=True, b_mn=True, out_dtype=torch.float32)               # [F,H]
+        db1, = _bgrad((b1,), dz)
+        dW1, = _wgrad((W1,), dz, xc)                                                         # [F,H]
         dx32 = ops.gemm(dz, W1_c, b_mn=True, res=dpre32, out_dtype=torch.float32)           # [M,H]
         return dx32, None, dW1, db1, dW2, db2, dgamma, dbeta, None, None, None
 
@@ -203,6 +305,7 @@ class PanoLayerFn(torch.autograd.Function):
         out32 = ops.gemm(h, W2_c, bias=b2, res=y32, out_dtype=torch.float32, drop_p=cfg.hid_p, drop_seed=cfg.seed + 3,
                          seed_ptr=cfg.seed_ptr)
         ctx.cfg = cfg
+        ctx.params = (Win, bin_, Wout, bout, W1, b1, W2, b2, g1, be1, g2, be2)
         ctx.save_for_backward(x32, x2c, qkv, o2, lse, y32, y2c, z, h, mean1, rstd1, mean2, rstd2, kmask, Win_c, Wout_c,
                               W1_c, W2_c, g1, g2)
         return out32
@@ -220,29 +323,30 @@ class PanoLayerFn(torch.autograd.Function):
         # FFN half
         dout_c = ops.cast(dout32, cdt, drop_p=p, drop_seed=cfg.seed + 3, seed_ptr=sp) if (p > 0 or cdt != torch.float32) \
             else dout32
-        db2 = ops.colsum(dout_c)
-        dW2 = ops.gemm(dout_c, h, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        Win, bin_, Wout, bout, W1, b1, W2, b2, g1p, be1p, g2p, be2p = ctx.params
+        db2, = _bgrad((b2,), dout_c)
+        dW2, = _wgrad((W2,), dout_c, h)
         dz = ops.gemm(dout_c, W2_c, b_mn=True, act=ops.ACT_DGELU, aux_in=z, out_dtype=cdt, drop_p=p,
                       drop_seed=cfg.seed + 2, seed_ptr=sp)
-        db1 = ops.colsum(dz)
-        dW1 = ops.gemm(dz, y2c, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        db1, = _bgrad((b1,), dz)
+        dW1, = _wgrad((W1,), dz, y2c)
         dy2 = ops.gemm(dz, W1_c, b_mn=True, out_dtype=torch.float32)
-        dy32, _, dg2, dbe2, _ = ops.layernorm_bwd(dy2, y32, g2, mean2, rstd2, dout32, True, None)
+        dy32, _, dg2, dbe2, _ = _ln_bwd(dy2, y32, g2, mean2, rstd2, dout32, None, 0.0, 0, None, g2p, be2p)
         # attention half
         dy_c = ops.cast(dy32, cdt, drop_p=p, drop_seed=cfg.seed + 1, seed_ptr=sp) if (p > 0 or cdt != torch.float32) \
             else dy32
-        dbout = ops.colsum(dy_c)
-        dWout = ops.gemm(dy_c, o2, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dbout, = _bgrad((bout,), dy_c)
+        dWout, = _wgrad((Wout,), dy_c, o2)
         do2 = ops.gemm(dy_c, Wout_c, b_mn=True, out_dtype=cdt)
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(do2.view(B, N, H), qkv[:, :H].unflatten(0, (B, N)), qkv[:, H:2 * H].unflatten(0, (B, N)),
                      qkv[:, 2 * H:].unflatten(0, (B, N)), o2.view(B, N, H), lse, cfg.heads,
                      dqkv[:, :H].unflatten(0, (B, N)), dqkv[:, H:2 * H].unflatten(0, (B, N)),
                      dqkv[:, 2 * H:].unflatten(0, (B, N)), kmask, None, 0.125, p, cfg.seed, sp)
-        dbin = ops.colsum(dqkv)
-        dWin = ops.gemm(dqkv, x2c, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        dbin, = _bgrad((bin_,), dqkv)
+        dWin, = _wgrad((Win,), dqkv, x2c)
         dx2 = ops.gemm(dqkv, Win_c, b_mn=True, out_dtype=torch.float32)
-        dx32, _, dg1, dbe1, _ = ops.layernorm_bwd(dx2, x32, g1, mean1, rstd1, dy32, True, None)
+        dx32, _, dg1, dbe1, _ = _ln_bwd(dx2, x32, g1, mean1, rstd1, dy32, None, 0.0, 0, None, g1p, be1p)
         return (dx32, None, dWin, dbin, dWout, dbout, dW1, db1, dW2, db2, dg1, dbe1, dg2, dbe2, None, None, None, None,
                 None)
 
@@ -264,6 +368,7 @@ class LinearFn(torch.autograd.Function):
             aux = torch.empty((xc.shape[0], W.shape[0]), device=xc.device, dtype=cdt)
         y = ops.gemm(xc, W_c, bias=b, act=act, aux_out=aux, out_dtype=torch.float32)
         ctx.act, ctx.cdt = act, cdt
+        ctx.params = (W, b)
         ctx.has_bias = b is not None
         ctx.save_for_backward(xc, W_c, y if act in (ops.ACT_RELU, ops.ACT_TANH) else None, aux)
         return y
@@ -281,8 +386,9 @@ class LinearFn(torch.autograd.Function):
             a = aux.float()
             dy = dy * (0.5 * (1.0 + torch.erf(a * 0.7071067811865476)) + a * torch.exp(-0.5 * a * a) * 0.3989422804014327)
         dyc = dy if cdt == torch.float32 else ops.cast(dy, cdt)
-        db = ops.colsum(dyc) if ctx.has_bias else None
-        dW = ops.gemm(dyc, xc, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        W, b = ctx.params
+        db, = _bgrad((b,), dyc)
+        dW, = _wgrad((W,), dyc, xc)
         dx = ops.gemm(dyc, W_c, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
         return dx, None, dW, db, None, None, None
 
@@ -293,6 +399,7 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x32, gamma, beta, eps, cdt):
         y32, y16, mean, rstd = ops.layernorm_fwd(x32, gamma, beta, eps, True, _d16(cdt))
+        ctx.params = (gamma, beta)
         ctx.save_for_backward(x32, gamma, mean, rstd)
         if y16 is not None:
             ctx.mark_non_differentiable(y16)
@@ -301,5 +408,6 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _d16):
         x32, gamma, mean, rstd = ctx.saved_tensors
-        dx32, _, dg, db, _ = ops.layernorm_bwd(dy.contiguous(), x32, gamma, mean, rstd, None, True, None)
+        dx32, _, dg, db, _ = _ln_bwd(dy.contiguous(), x32, gamma, mean, rstd, None, None, 0.0, 0, None, ctx.params[0],
+                                     ctx.params[1])
         return dx32, dg, db, None, None

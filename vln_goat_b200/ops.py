@@ -10,6 +10,11 @@ import torch
 from . import _lib
 from ._lib import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F16, F32  # noqa: F401
 
+# kernels launched by this library since import (bench.py reports the per-step delta as gpu_launches)
+LAUNCHES = [0]
+# when set to a list, every gemm() call appends (M, N, K, a_mn, b_mn, dtype code, ran_on_simt) -- bench.py's roofline pass
+GEMM_LOG = None
+
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
 
@@ -83,6 +88,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
     a.drop_seed_ptr = None if seed_ptr is None else seed_ptr.data_ptr()
     a.force_simt = int(force_simt)
     _lib.check(_lib.lib().goat_gemm(C.byref(a), _stream()), "goat_gemm")
+    LAUNCHES[0] += 1
+    if GEMM_LOG is not None:
+        umma = a.dtype != F32 and K >= 16 and K % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and not force_simt
+        GEMM_LOG.append((M, N, K, int(a_mn), int(b_mn), a.dtype, int(not umma)))
     return out
 
 
@@ -127,6 +136,7 @@ def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, dro
     lse = torch.empty((B, heads, Nq), device=q.device, dtype=torch.float32)
     a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr)
     _lib.check(_lib.lib().goat_attn_core_fwd(C.byref(a), _stream()), "goat_attn_core_fwd")
+    LAUNCHES[0] += 1
     return o, lse
 
 
@@ -144,6 +154,7 @@ def attn_bwd(do, q, k, v, o, lse, heads, dq, dk, dv, kmask=None, bias=None, scal
         dbias = torch.zeros((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
         a.dbias = dbias.data_ptr()
     _lib.check(_lib.lib().goat_attn_core_bwd(C.byref(a), _stream()), "goat_attn_core_bwd")
+    LAUNCHES[0] += 2
     return dbias
 
 
@@ -160,12 +171,14 @@ def layernorm_fwd(x, gamma, beta, eps, want32=True, dtype16=None):
     rc = _lib.lib().goat_layernorm_fwd(_p(x), dt(x), _p(gamma), _p(beta), eps, _p(y32), _p(y16),
                                        dt(dtype16) if dtype16 is not None else F16, _p(mean), _p(rstd), M, H, _stream())
     _lib.check(rc, "goat_layernorm_fwd")
+    LAUNCHES[0] += 1
     return y32, y16, mean, rstd
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None, drop_p=0.0, drop_seed=0,
-                  seed_ptr=None, want_colsum=False):
-    """-> (dx32 or None, dx16 or None, dgamma [H], dbeta [H], dcolsum [H] or None)"""
+                  seed_ptr=None, want_colsum=False, dgamma_out=None, dbeta_out=None, dcol_out=None):
+    """-> (dx32 or None, dx16 or None, dgamma [H], dbeta [H], dcolsum [H] or None)
+    *_out: optional contiguous fp32 [H] destinations (e.g. flat gradient views) written instead of new tensors."""
     _req_cuda(dy, x, gamma, mean, rstd, dres)
     M, H = x.shape
     if dy.dtype != torch.float32 or not dy.is_contiguous() or tuple(dy.shape) != (M, H):
@@ -173,14 +186,19 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None
     dev = x.device
     dx32 = torch.empty((M, H), device=dev, dtype=torch.float32) if want32 else None
     dx16 = torch.empty((M, H), device=dev, dtype=dtype16) if dtype16 is not None else None
-    dgamma = torch.empty((H,), device=dev, dtype=torch.float32)
-    dbeta = torch.empty((H,), device=dev, dtype=torch.float32)
-    dcol = torch.empty((H,), device=dev, dtype=torch.float32) if want_colsum else None
+    for o in (dgamma_out, dbeta_out, dcol_out):
+        if o is not None and (o.dtype != torch.float32 or o.numel() != H or not o.is_contiguous()):
+            raise ValueError("layernorm_bwd: *_out must be contiguous fp32 [H]")
+    dgamma = dgamma_out if dgamma_out is not None else torch.empty((H,), device=dev, dtype=torch.float32)
+    dbeta = dbeta_out if dbeta_out is not None else torch.empty((H,), device=dev, dtype=torch.float32)
+    dcol = (dcol_out if dcol_out is not None else torch.empty((H,), device=dev, dtype=torch.float32)) \
+        if want_colsum else None
     ws = torch.empty((_lib.lib().goat_layernorm_bwd_workspace_bytes(M, H),), device=dev, dtype=torch.uint8)
     rc = _lib.lib().goat_layernorm_bwd(_p(dy), _p(x), dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
                                        dt(dtype16) if dtype16 is not None else F16, drop_p, drop_seed, _p(seed_ptr),
                                        _p(dgamma), _p(dbeta), _p(dcol), _p(ws), M, H, _stream())
     _lib.check(rc, "goat_layernorm_bwd")
+    LAUNCHES[0] += 2
     return dx32, dx16, dgamma, dbeta, dcol
 
 
@@ -195,6 +213,7 @@ def colsum(x, out=None):
         raise ValueError("colsum: out must be contiguous fp32 [N]")
     ws = torch.empty((_lib.lib().goat_colsum_workspace_bytes(M, N),), device=x.device, dtype=torch.uint8)
     _lib.check(_lib.lib().goat_colsum(_p(x), dt(x), M, N, ld, _p(out), _p(ws), _stream()), "goat_colsum")
+    LAUNCHES[0] += 2
     return out
 
 
@@ -209,4 +228,5 @@ def cast(src, dtype, out=None, drop_p=0.0, drop_seed=0, seed_ptr=None):
         raise ValueError("cast: bad out")
     _lib.check(_lib.lib().goat_dropout_cast(_p(src), dt(src), _p(out), dt(out), src.numel(), drop_p, drop_seed,
                                             _p(seed_ptr), _stream()), "goat_dropout_cast")
+    LAUNCHES[0] += 1
     return out
