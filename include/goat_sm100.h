@@ -102,7 +102,9 @@ int goat_gemm(const goat_gemm_args* args, goat_stream_t stream);
  * P/model/ops.py:25-34, or -inf for the pano encoder's key_padding_mask); bias is the additive
  * [B,Nq,Nk] term (graph_sprels, :690-691).  lse[b,h,q] (log-sum-exp of the scaled scores) is
  * saved for backward.  drop_p/seed: attention-probability dropout (:280).
- * D must be 64.
+ * D must be 64.  F16/BF16 with Nq <= 128, 16-byte aligned bases and ld/sb multiples of 8 run on tcgen05
+ * (TMA-staged Q/K/V tiles, S and O accumulators in TMEM, keys in chunks of 128); everything else, and F32,
+ * runs the fp32-math SIMT kernels.
  * ------------------------------------------------------------------------------------------ */
 typedef struct goat_attn_args {
   int B, heads, Nq, Nk, D;
@@ -128,6 +130,7 @@ typedef struct goat_attn_args {
   void* dK;       /* same layout as K */
   void* dV;       /* same layout as V */
   float* dbias;   /* [B, Nq, Nk] fp32, ACCUMULATED into (caller zeroes), or NULL */
+  int force_simt; /* 1: run the fp32-math SIMT kernels even when the tcgen05 path is eligible (cross-check) */
 } goat_attn_args;
 int goat_attn_core_fwd(const goat_attn_args* args, goat_stream_t stream);
 int goat_attn_core_bwd(const goat_attn_args* args, goat_stream_t stream);

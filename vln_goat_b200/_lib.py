@@ -45,6 +45,7 @@ class AttnArgs(C.Structure):
         ("drop_p", C.c_float), ("drop_seed", C.c_uint64), ("drop_seed_ptr", C.c_void_p),
         ("dO", C.c_void_p), ("dQ", C.c_void_p), ("dK", C.c_void_p), ("dV", C.c_void_p),
         ("dbias", C.c_void_p),
+        ("force_simt", C.c_int),
     ]
 
 

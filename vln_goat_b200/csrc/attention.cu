@@ -399,6 +399,10 @@ int check_args(const goat_attn_args* a, bool bwd) {
 
 }  // namespace
 
+bool attn_tc_eligible(const goat_attn_args* a, bool bwd);
+int attn_fwd_tc(const goat_attn_args* a, cudaStream_t st);
+int attn_bwd_tc(const goat_attn_args* a, cudaStream_t st);
+
 }  // namespace goat
 
 using namespace goat;
@@ -409,6 +413,7 @@ extern "C" int goat_attn_core_fwd(const goat_attn_args* a, goat_stream_t stream)
   if (a->B == 0 || a->Nq == 0) return GOAT_OK;
   GOAT_CHECK(a->Nk > 0, "goat_attn_core_fwd: Nk must be > 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!a->force_simt && attn_tc_eligible(a, false)) return attn_fwd_tc(a, st);
   if (a->dtype == GOAT_F32) return fwd_t<float>(*a, st);
   if (a->dtype == GOAT_F16) return fwd_t<__half>(*a, st);
   return fwd_t<__nv_bfloat16>(*a, st);
@@ -419,6 +424,7 @@ extern "C" int goat_attn_core_bwd(const goat_attn_args* a, goat_stream_t stream)
   if (rc) return rc;
   if (a->B == 0 || a->Nq == 0 || a->Nk == 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!a->force_simt && attn_tc_eligible(a, true)) return attn_bwd_tc(a, st);
   if (a->dtype == GOAT_F32) return bwd_t<float>(*a, st);
   if (a->dtype == GOAT_F16) return bwd_t<__half>(*a, st);
   return bwd_t<__nv_bfloat16>(*a, st);

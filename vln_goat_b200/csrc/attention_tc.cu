@@ -1,0 +1,572 @@
+// Attention core on the 5th-gen tensor cores (fp16 / bf16 operands, fp32 accumulation in TMEM).
+//
+//   forward : O = softmax(scale Q K^T + kmask + bias) V, lse saved
+//   backward: P recomputed from lse;  dV = P~^T dO,  dS = P (dP~ - delta),  dQ = scale dS K,  dK = scale dS^T Q
+//
+// One CTA (128 threads = 128 TMEM lanes = 128 query rows) per (head, batch); keys are processed in chunks of
+// 128.  Q / K / V / dO tiles are fetched by 3-D TMA (inner = head slice of 64 channels, token, batch; out-of-range
+// tokens are zero-filled) straight from the token-major [B, N, heads*64] tensors into 128B-swizzled shared memory.
+// Every contraction is a tcgen05.mma with M = 128:
+//     S  = Q K^T      A = Q  (K-major)   B = K  (K-major)    N = keys
+//     O  = P V        A = P  (K-major)   B = V  (MN-major)   N = 64
+//     dP = dO V^T     A = dO (K-major)   B = V  (K-major)    N = keys
+//     dV = P^T dO     A = P  (MN-major)  B = dO (MN-major)   N = 64   (M = keys)
+//     dK = dS^T Q     A = dS (MN-major)  B = Q  (MN-major)   N = 64   (M = keys)
+//     dQ = dS K       A = dS (K-major)   B = K  (MN-major)   N = 64
+// A [rows][64 x 16-bit] tile with the 128-byte swizzle is simultaneously the canonical K-major layout (rows = M/N,
+// 64 contiguous = K) and the canonical MN-major layout (rows = K, 64 contiguous = M/N), so P / dS / Q / K / V / dO
+// are each staged once and read both ways.  The softmax runs on the TMEM rows (thread r owns query r: tcgen05.ld,
+// exp, row sums in registers), writes P (and dS) as 16-bit operands back to shared memory for the second MMA.
+// TMEM budget: 256 columns (S 128 + O 64 forward; S 128 + dP 128, then reused for dV 64 | dK 64 | dQ 64 backward).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace goat {
+
+int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
+               uint64_t sb_elems, uint32_t box0, uint32_t box1);
+
+namespace {
+
+constexpr int TC_THREADS = 128;
+constexpr int KC = 128;               // keys per chunk
+constexpr int TILE = 128 * 128;       // bytes of a [128 rows][64 x 2 B] tile
+constexpr int TMEM_COLS = 256;
+
+struct TcArgs {
+  int B, heads, Nq, Nk;
+  const float* kmask;
+  const float* bias;
+  float scale;
+  float* lse;
+  float drop_p;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_ptr;
+  void* O; int ldo; long long sbo;      // forward output / backward: forward output (for delta)
+  const void* dO;                        // backward (same layout as O)
+  void* dQ; int ldq; long long sbq;
+  void* dK; int ldk; long long sbk;
+  void* dV; int ldv; long long sbv;
+  float* dbias;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// address of 16-byte chunk `q` (8 elements) of row `r` inside a [rows][64] 128B-swizzled tile
+__device__ __forceinline__ uint8_t* sw_chunk(uint8_t* tile, int r, int q) { return tile + r * 128 + ((q ^ (r & 7)) << 4); }
+
+// store 32 consecutive fp32 values (columns c0 .. c0+31 of row r) as 16-bit into the [2 blocks][128 rows][64] operand
+template <typename T>
+__device__ __forceinline__ void store_row32(uint8_t* buf, int r, int c0, const float (&v)[32]) {
+  uint8_t* tile = buf + (c0 >> 6) * TILE;
+  const int q0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 w;
+    w.x = pack2<T>(v[q * 8 + 0], v[q * 8 + 1]);
+    w.y = pack2<T>(v[q * 8 + 2], v[q * 8 + 3]);
+    w.z = pack2<T>(v[q * 8 + 4], v[q * 8 + 5]);
+    w.w = pack2<T>(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(sw_chunk(tile, r, q0 + q)) = w;
+  }
+}
+
+// write 64 fp32 values as one 128-byte row of 16-bit elements to global memory
+template <typename T>
+__device__ __forceinline__ void store_global_row64(T* dst, const float* v, float mul) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 w;
+    w.x = pack2<T>(v[q * 8 + 0] * mul, v[q * 8 + 1] * mul);
+    w.y = pack2<T>(v[q * 8 + 2] * mul, v[q * 8 + 3] * mul);
+    w.z = pack2<T>(v[q * 8 + 4] * mul, v[q * 8 + 5] * mul);
+    w.w = pack2<T>(v[q * 8 + 6] * mul, v[q * 8 + 7] * mul);
+    d[q] = w;
+  }
+}
+
+__device__ __forceinline__ float drop_mul(const TcArgs& p, unsigned long long seed, int b, int h, int qi, int kj) {
+  const unsigned long long idx =
+      (((unsigned long long)b * p.heads + h) * p.Nq + qi) * (unsigned long long)p.Nk + kj;
+  return rand_uniform(seed, idx) >= p.drop_p ? 1.f / (1.f - p.drop_p) : 0.f;
+}
+
+struct Smem {
+  uint8_t* base;
+  __device__ explicit Smem(uint8_t* raw) {
+    base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+constexpr int FWD_SMEM = 3 * TILE + 2 * TILE + 64 + 1024;  // Q K V | P(2 blocks) | barriers | alignment
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm(smem_raw);
+  uint8_t* sQ = sm.base;
+  uint8_t* sK = sQ + TILE;
+  uint8_t* sV = sK + TILE;
+  uint8_t* sP = sV + TILE;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + 2 * TILE);
+  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_mma = bar_q + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr int FMT = UmmaFmt<T>::value;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, TILE);
+    tma_load_3d(sQ, &tmQ, bar_q, h * 64, 0, b);
+  }
+  const int r = tid;
+  const bool rv = r < p.Nq;
+  const bool warp_live = warp * 32 < p.Nq;
+  const float* brow = p.bias ? p.bias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
+  const float* krow = p.kmask ? p.kmask + (long long)b * p.Nk : nullptr;
+  const unsigned long long seed = p.drop_p > 0.f ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
+  const int nchunks = (p.Nk + KC - 1) / KC;
+  uint32_t ph_kv = 0, ph_mma = 0;
+  float m = -INFINITY, l = 0.f;
+
+  // S[128 x nk16] = Q K_c^T into TMEM columns [0, nk16)
+  auto issue_qk = [&](int nk16) {
+    const uint32_t idesc = make_idesc_f16(FMT, 0, 0, 128, nk16);
+    const uint32_t a0 = smem_u32(sQ), b0 = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_f16(tmem, make_smem_desc_sw128(a0 + k * 32, 0, 1024), make_smem_desc_sw128(b0 + k * 32, 0, 1024), idesc,
+               k ? 1u : 0u);
+  };
+  auto score = [&](float acc, int key) -> float {
+    float s = acc * p.scale;
+    if (krow) s += __ldg(krow + key);
+    if (brow) s += __ldg(brow + key);
+    return s;
+  };
+
+  // ---- pass A (only when the keys do not fit one chunk): exact row maxima
+  if (nchunks > 1) {
+    for (int c = 0; c < nchunks; ++c) {
+      const int nk = min(KC, p.Nk - c * KC), nk16 = (nk + 15) & ~15;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar_kv, TILE);
+        tma_load_3d(sK, &tmK, bar_kv, h * 64, c * KC, b);
+        if (c == 0) mbar_wait(bar_q, 0);
+        mbar_wait(bar_kv, ph_kv);
+        tcgen05_fence_after();
+        issue_qk(nk16);
+        umma_commit(bar_mma);
+      }
+      ph_kv ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tcgen05_fence_after();
+      if (warp_live) {
+        for (int g = 0; g * 32 < nk; ++g) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(t_row + g * 32, rr);
+          tmem_ld_wait();
+          if (rv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int key = c * KC + g * 32 + j;
+              if (key < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), key));
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncthreads();
+    }
+  }
+
+  // ---- pass B: P = exp(S - m), O += P V
+  for (int c = 0; c < nchunks; ++c) {
+    const int nk = min(KC, p.Nk - c * KC), nk16 = (nk + 15) & ~15;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_kv, 2 * TILE);
+      tma_load_3d(sK, &tmK, bar_kv, h * 64, c * KC, b);
+      tma_load_3d(sV, &tmV, bar_kv, h * 64, c * KC, b);
+      if (c == 0 && nchunks == 1) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph_kv);
+      tcgen05_fence_after();
+      issue_qk(nk16);
+      umma_commit(bar_mma);
+    }
+    ph_kv ^= 1;
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tcgen05_fence_after();
+    if (warp_live) {
+      if (nchunks == 1) {
+        for (int g = 0; g * 32 < nk; ++g) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(t_row + g * 32, rr);
+          tmem_ld_wait();
+          if (rv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int key = g * 32 + j;
+              if (key < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), key));
+            }
+          }
+        }
+      }
+      const float mref = (m == -INFINITY) ? 0.f : m;
+      for (int g = 0; g * 32 < nk16; ++g) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(t_row + g * 32, rr);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c * KC + g * 32 + j;
+          float e = 0.f;
+          if (rv && key < p.Nk) {
+            e = __expf(score(__uint_as_float(rr[j]), key) - mref);
+            l += e;
+            if (p.drop_p > 0.f) e *= drop_mul(p, seed, b, h, r, key);
+          }
+          pv[j] = e;
+        }
+        store_row32<T>(sP, r, g * 32, pv);
+      }
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_f16(FMT, 0, 1, 128, 64);
+      const uint32_t a0 = smem_u32(sP), b0 = smem_u32(sV);
+      for (int kk = 0; kk * 16 < nk16; ++kk)
+        umma_f16(tmem + 128, make_smem_desc_sw128(a0 + (kk >> 2) * TILE + (kk & 3) * 32, 0, 1024),
+                 make_smem_desc_sw128(b0 + kk * 2048, 8192, 1024), idesc, (c | kk) ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tcgen05_fence_after();
+  }
+
+  // ---- epilogue: O / l -> global, lse
+  if (warp_live) {
+    float o[64];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(t_row + 128 + g * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[g * 32 + j] = __uint_as_float(rr[j]);
+    }
+    if (rv) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      T* dst = reinterpret_cast<T*>(p.O) + (long long)b * p.sbo + (long long)r * p.ldo + h * 64;
+      store_global_row64<T>(dst, o, inv);
+      if (p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + r] = l > 0.f ? m + __logf(l) : -INFINITY;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+constexpr int BWD_SMEM = 4 * TILE + 4 * TILE + 64 + 1024;  // Q dO K V | P(2) dS(2) | barriers | alignment
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm(smem_raw);
+  uint8_t* sQ = sm.base;
+  uint8_t* sdO = sQ + TILE;
+  uint8_t* sK = sdO + TILE;
+  uint8_t* sV = sK + TILE;
+  uint8_t* sP = sV + TILE;
+  uint8_t* sdS = sP + 2 * TILE;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sdS + 2 * TILE);
+  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_mma = bar_q + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr int FMT = UmmaFmt<T>::value;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 2 * TILE);
+    tma_load_3d(sQ, &tmQ, bar_q, h * 64, 0, b);
+    tma_load_3d(sdO, &tmdO, bar_q, h * 64, 0, b);
+  }
+  const int r = tid;
+  const bool rv = r < p.Nq;
+  const float* brow = p.bias ? p.bias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
+  const float* krow = p.kmask ? p.kmask + (long long)b * p.Nk : nullptr;
+  float* dbrow = p.dbias ? p.dbias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
+  const unsigned long long seed = p.drop_p > 0.f ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
+  const int nchunks = (p.Nk + KC - 1) / KC;
+  const int nq16 = (min(p.Nq, 128) + 15) & ~15;
+
+  // delta_r = sum_d dO[r,d] O[r,d];  lse_r
+  float delta = 0.f, lse = 0.f;
+  if (rv) {
+    const long long off = (long long)b * p.sbo + (long long)r * p.ldo + h * 64;
+    const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.O) + off);
+    const uint4* pg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dO) + off);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 a = __ldg(po + q), g = __ldg(pg + q);
+      float2 x, y;
+      x = unpack2<T>(a.x); y = unpack2<T>(g.x); delta += x.x * y.x + x.y * y.y;
+      x = unpack2<T>(a.y); y = unpack2<T>(g.y); delta += x.x * y.x + x.y * y.y;
+      x = unpack2<T>(a.z); y = unpack2<T>(g.z); delta += x.x * y.x + x.y * y.y;
+      x = unpack2<T>(a.w); y = unpack2<T>(g.w); delta += x.x * y.x + x.y * y.y;
+    }
+    lse = p.lse[((long long)b * p.heads + h) * p.Nq + r];
+  }
+  float dq[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) dq[j] = 0.f;
+
+  uint32_t ph_kv = 0, ph_mma = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int nk = min(KC, p.Nk - c * KC), nk16 = (nk + 15) & ~15;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_kv, 2 * TILE);
+      tma_load_3d(sK, &tmK, bar_kv, h * 64, c * KC, b);
+      tma_load_3d(sV, &tmV, bar_kv, h * 64, c * KC, b);
+      if (c == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph_kv);
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_f16(FMT, 0, 0, 128, nk16);
+      const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO), v0 = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // S = Q K^T -> cols [0,128)
+        umma_f16(tmem, make_smem_desc_sw128(q0 + k * 32, 0, 1024), make_smem_desc_sw128(k0 + k * 32, 0, 1024), idesc,
+                 k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // dP = dO V^T -> cols [128,256)
+        umma_f16(tmem + 128, make_smem_desc_sw128(g0 + k * 32, 0, 1024), make_smem_desc_sw128(v0 + k * 32, 0, 1024),
+                 idesc, k ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    ph_kv ^= 1;
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tcgen05_fence_after();
+
+    for (int g = 0; g * 32 < nk16; ++g) {
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32b_x32(t_row + g * 32, rs);
+      tmem_ld_32x32b_x32(t_row + 128 + g * 32, rp);
+      tmem_ld_wait();
+      float pv[32], dsv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int key = c * KC + g * 32 + j;
+        float pd = 0.f, ds = 0.f;
+        if (rv && key < p.Nk) {
+          float s = __uint_as_float(rs[j]) * p.scale;
+          if (krow) s += __ldg(krow + key);
+          if (brow) s += __ldg(brow + key);
+          const float pr = __expf(s - lse);
+          const float dm = p.drop_p > 0.f ? drop_mul(p, seed, b, h, r, key) : 1.f;
+          pd = pr * dm;
+          ds = pr * (__uint_as_float(rp[j]) * dm - delta);
+          if (dbrow) atomicAdd(dbrow + key, ds);
+        }
+        pv[j] = pd;
+        dsv[j] = ds;
+      }
+      store_row32<T>(sP, r, g * 32, pv);
+      store_row32<T>(sdS, r, g * 32, dsv);
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), q0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO);
+      const uint32_t id_tt = make_idesc_f16(FMT, 1, 1, 128, 64);
+      const uint32_t id_nt = make_idesc_f16(FMT, 0, 1, 128, 64);
+      for (int kq = 0; kq * 16 < nq16; ++kq)   // dV[key, d] = sum_q P[q,key] dO[q,d]   -> cols [0,64)
+        umma_f16(tmem, make_smem_desc_sw128(pa + kq * 2048, TILE, 1024), make_smem_desc_sw128(g0 + kq * 2048, 8192, 1024),
+                 id_tt, kq ? 1u : 0u);
+      for (int kq = 0; kq * 16 < nq16; ++kq)   // dK[key, d] = sum_q dS[q,key] Q[q,d]  -> cols [64,128)
+        umma_f16(tmem + 64, make_smem_desc_sw128(sa + kq * 2048, TILE, 1024),
+                 make_smem_desc_sw128(q0 + kq * 2048, 8192, 1024), id_tt, kq ? 1u : 0u);
+      for (int kk = 0; kk * 16 < nk16; ++kk)   // dQ[q, d] = sum_key dS[q,key] K[key,d]  -> cols [128,192)
+        umma_f16(tmem + 128, make_smem_desc_sw128(sa + (kk >> 2) * TILE + (kk & 3) * 32, 0, 1024),
+                 make_smem_desc_sw128(k0 + kk * 2048, 8192, 1024), id_nt, kk ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tcgen05_fence_after();
+
+    {
+      const int key = c * KC + tid;   // this thread's TMEM lane is a KEY for dV / dK
+      const bool kv = tid < nk;
+      float t[64];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(t_row + g * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+      }
+      if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dV) + (long long)b * p.sbv + (long long)key * p.ldv + h * 64, t, 1.f);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(t_row + 64 + g * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+      }
+      if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dK) + (long long)b * p.sbk + (long long)key * p.ldk + h * 64, t, p.scale);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(t_row + 128 + g * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dq[g * 32 + j] += __uint_as_float(rr[j]);
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+  }
+  if (rv) store_global_row64<T>(reinterpret_cast<T*>(p.dQ) + (long long)b * p.sbq + (long long)r * p.ldq + h * 64, dq, p.scale);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+int fill(const goat_attn_args* a, TcArgs* t) {
+  t->B = a->B; t->heads = a->heads; t->Nq = a->Nq; t->Nk = a->Nk;
+  t->kmask = a->kmask; t->bias = a->bias; t->scale = a->scale; t->lse = a->lse;
+  t->drop_p = a->drop_p; t->drop_seed = a->drop_seed;
+  t->drop_seed_ptr = reinterpret_cast<const unsigned long long*>(a->drop_seed_ptr);
+  t->O = a->O; t->ldo = a->ldo; t->sbo = a->sbo;
+  t->dO = a->dO;
+  t->dQ = a->dQ; t->ldq = a->ldq; t->sbq = a->sbq;
+  t->dK = a->dK; t->ldk = a->ldk; t->sbk = a->sbk;
+  t->dV = a->dV; t->ldv = a->ldv; t->sbv = a->sbv;
+  t->dbias = a->dbias;
+  return GOAT_OK;
+}
+
+template <typename T>
+int fwd_launch(const goat_attn_args* a, cudaStream_t st) {
+  static bool cfg = false;
+  if (!cfg) {
+    GOAT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    cfg = true;
+  }
+  CUtensorMap tq, tk, tv;
+  int rc;
+  const uint64_t cols = (uint64_t)a->heads * 64;
+  if ((rc = make_tmap3(&tq, a->dtype, a->Q, cols, a->Nq, a->B, a->ldq, a->sbq, 64, 128))) return rc;
+  if ((rc = make_tmap3(&tk, a->dtype, a->K, cols, a->Nk, a->B, a->ldk, a->sbk, 64, 128))) return rc;
+  if ((rc = make_tmap3(&tv, a->dtype, a->V, cols, a->Nk, a->B, a->ldv, a->sbv, 64, 128))) return rc;
+  TcArgs t;
+  fill(a, &t);
+  dim3 grid(a->heads, a->B);
+  attn_fwd_tc_kernel<T><<<grid, TC_THREADS, FWD_SMEM, st>>>(tq, tk, tv, t);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+template <typename T>
+int bwd_launch(const goat_attn_args* a, cudaStream_t st) {
+  static bool cfg = false;
+  if (!cfg) {
+    GOAT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    cfg = true;
+  }
+  CUtensorMap tq, tk, tv, tg;
+  int rc;
+  const uint64_t cols = (uint64_t)a->heads * 64;
+  if ((rc = make_tmap3(&tq, a->dtype, a->Q, cols, a->Nq, a->B, a->ldq, a->sbq, 64, 128))) return rc;
+  if ((rc = make_tmap3(&tk, a->dtype, a->K, cols, a->Nk, a->B, a->ldk, a->sbk, 64, 128))) return rc;
+  if ((rc = make_tmap3(&tv, a->dtype, a->V, cols, a->Nk, a->B, a->ldv, a->sbv, 64, 128))) return rc;
+  if ((rc = make_tmap3(&tg, a->dtype, a->dO, cols, a->Nq, a->B, a->ldo, a->sbo, 64, 128))) return rc;
+  TcArgs t;
+  fill(a, &t);
+  dim3 grid(a->heads, a->B);
+  attn_bwd_tc_kernel<T><<<grid, TC_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tg, t);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+bool ok16(const void* p, long long ld, long long sb) {
+  return aligned16(p) && (ld % 8) == 0 && (sb % 8) == 0 && ld >= 64 && sb >= 0;
+}
+
+}  // namespace
+
+// The tensor-core path takes 16-bit operands, up to 128 query rows per (head, batch) and TMA-compatible strides.
+bool attn_tc_eligible(const goat_attn_args* a, bool bwd) {
+  if (a->dtype != GOAT_F16 && a->dtype != GOAT_BF16) return false;
+  if (a->Nq > 128 || a->Nq < 1 || a->Nk < 1 || a->D != 64) return false;
+  if (a->heads > 65535 || a->B > 65535) return false;
+  if (a->B > 1 && (a->sbq <= 0 || a->sbk <= 0 || a->sbv <= 0 || a->sbo <= 0)) return false;  // broadcast operands
+  if (!ok16(a->Q, a->ldq, a->sbq) || !ok16(a->K, a->ldk, a->sbk) || !ok16(a->V, a->ldv, a->sbv) ||
+      !ok16(a->O, a->ldo, a->sbo))
+    return false;
+  if (bwd && (!ok16(a->dO, a->ldo, a->sbo) || !aligned16(a->dQ) || !aligned16(a->dK) || !aligned16(a->dV))) return false;
+  return true;
+}
+
+int attn_fwd_tc(const goat_attn_args* a, cudaStream_t st) {
+  return a->dtype == GOAT_F16 ? fwd_launch<__half>(a, st) : fwd_launch<__nv_bfloat16>(a, st);
+}
+int attn_bwd_tc(const goat_attn_args* a, cudaStream_t st) {
+  return a->dtype == GOAT_F16 ? bwd_launch<__half>(a, st) : bwd_launch<__nv_bfloat16>(a, st);
+}
+
+}  // namespace goat

@@ -284,6 +284,29 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint
   return GOAT_OK;
 }
 
+}  // namespace
+
+// 3-D map over a token-major [d2 = batch][d1 = token][d0 = channel] tensor (channel contiguous, token stride ld,
+// batch stride sb, in elements); boxes of box0 channels x box1 tokens x 1 batch, 128B swizzle, zero OOB fill.
+int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
+               uint64_t sb_elems, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode_tiled();
+  GOAT_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[3] = {d0, d1, d2};
+  const cuuint64_t gstr[2] = {ld_elems * 2, (d2 > 1 ? sb_elems : (uint64_t)d1 * ld_elems) * 2};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = dtype == GOAT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(tm, dt, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GOAT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d (dims %llu %llu %llu ld %llu sb %llu)",
+             (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)ld_elems, (unsigned long long)sb_elems);
+  return GOAT_OK;
+}
+
+namespace {
+
 template <typename T, int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, STAGES>;

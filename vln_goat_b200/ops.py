@@ -102,7 +102,7 @@ def _tok3(t, name, heads):
     return t.stride(1), t.stride(0)
 
 
-def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr=None):
+def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr=None, force_simt=False):
     B, Nq, _ = q.shape
     Nk = k.shape[1]
     a = _lib.AttnArgs()
@@ -125,26 +125,28 @@ def _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, se
     a.lse = lse.data_ptr()
     a.drop_p, a.drop_seed = drop_p, drop_seed
     a.drop_seed_ptr = None if seed_ptr is None else seed_ptr.data_ptr()
+    a.force_simt = int(force_simt)
     return a
 
 
-def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0, seed_ptr=None):
+def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0, seed_ptr=None,
+             force_simt=False):
     """-> (O [B,Nq,heads*64] same dtype, lse [B,heads,Nq] fp32)"""
     _req_cuda(q, k, v, kmask, bias)
     B, Nq, _ = q.shape
     o = torch.empty((B, Nq, heads * 64), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, heads, Nq), device=q.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr)
+    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr, force_simt)
     _lib.check(_lib.lib().goat_attn_core_fwd(C.byref(a), _stream()), "goat_attn_core_fwd")
     LAUNCHES[0] += 1
     return o, lse
 
 
 def attn_bwd(do, q, k, v, o, lse, heads, dq, dk, dv, kmask=None, bias=None, scale=0.125, drop_p=0.0, drop_seed=0,
-             seed_ptr=None, want_dbias=False):
+             seed_ptr=None, want_dbias=False, force_simt=False):
     """dq/dk/dv: preallocated views with the same strides as q/k/v.  -> dbias [B,Nq,Nk] fp32 or None"""
     _req_cuda(do, q, k, v, o, lse, dq, dk, dv)
-    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr)
+    a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr, force_simt)
     for name, t, ref in (("dq", dq, q), ("dk", dk, k), ("dv", dv, v), ("do", do, o)):
         if t.stride() != ref.stride() or t.shape != ref.shape or t.dtype != ref.dtype:
             raise ValueError("attn_bwd: %s must match the layout of its forward tensor" % name)
