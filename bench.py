@@ -348,6 +348,7 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
     ts._fwd_bwd()  # eager pass: records (M,N,K,a_mn,b_mn) per launch and warms every shape
     ops.GEMM_LOG = None
     torch.cuda.synchronize()
+    ts.flat.g.zero_()
     uniq = {}
     for r in rec:
         uniq[r] = uniq.get(r, 0) + 1

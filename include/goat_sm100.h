@@ -63,6 +63,8 @@ int goat_device_supported(void);
  * dtype F16/BF16 -> tcgen05.mma (TMA-fed, TMEM accumulators) when K, lda, ldb are multiples of 8
  * and K >= 16; otherwise, and always for F32, the SIMT kernel.  force_simt=1 selects the SIMT
  * kernel (used by tests as an on-device cross-check).
+ * The tcgen05 kernel is persistent (one CTA per SM walking 128x128 tiles) with two TMEM accumulators so the
+ * epilogue of one tile overlaps the main loop of the next.
  * ------------------------------------------------------------------------------------------ */
 typedef struct goat_gemm_args {
   int M, N, K;
@@ -88,6 +90,9 @@ typedef struct goat_gemm_args {
   uint64_t drop_seed;
   const uint64_t* drop_seed_ptr; /* optional DEVICE word added to drop_seed at run time (CUDA-graph safe reseeding) */
   int force_simt;
+  int accumulate; /* 1: out (fp32) += alpha * A B^T, reduced with fp32 atomics; the tcgen05 kernel then also splits K
+                     across CTAs when M x N alone cannot fill the GPU (weight gradients: K = tokens).  No bias / res /
+                     act / dropout / out2 in this mode; the caller zero-initialises out. */
 } goat_gemm_args;
 int goat_gemm(const goat_gemm_args* args, goat_stream_t stream);
 
@@ -180,12 +185,14 @@ int goat_dropout_cast(const void* src, int src_dtype, void* dst, int dst_dtype, 
  *               shadow (optional, F16/BF16) = p rounded -- the operand copy the tcgen05 GEMMs read.
  *               hp is a DEVICE array of 9 floats {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t,
  *               max_grad_norm (<=0: off), grad pre-scale}; norm_out (optional, device) receives the norm.
+ *               zero_grad=1 also clears g (optimizer.zero_grad(), P/train_r2r_goat.py:366) so that the next
+ *               step's split-K weight-gradient GEMMs can accumulate into it with atomics.
  * ------------------------------------------------------------------------------------------ */
 size_t goat_sumsq_workspace_bytes(void);
 int goat_sumsq(const float* g, long long n, float* partial, int* nparts_out, goat_stream_t stream);
-int goat_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
+int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
                     long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
-                    goat_stream_t stream);
+                    int zero_grad, goat_stream_t stream);
 
 #ifdef __cplusplus
 }

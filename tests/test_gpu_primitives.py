@@ -25,7 +25,7 @@ OUT_TOL = {torch.float32: 2e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (2368, 2304, 768), (5120, 768, 3072), (77, 200, 72),
-                                   (2368, 768, 2368), (8, 8, 16)])
+                                   (2368, 768, 2368), (8, 8, 16), (768, 768, 5120), (768, 3072, 2368)])
 def test_gemm_umma_vs_fp64_and_simt(dtype, a_mn, b_mn, M, N, K):
     from vln_goat_b200 import ops
     if (a_mn and M % 8) or (b_mn and N % 8):
@@ -42,6 +42,10 @@ def test_gemm_umma_vs_fp64_and_simt(dtype, a_mn, b_mn, M, N, K):
     assert rel(out_s, ref) < 2e-5
     out16 = ops.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn)
     assert rel(out16, ref) < OUT_TOL[dtype]
+    # accumulate mode (split-K + fp32 atomics): twice into the same zero-initialised buffer
+    acc = ops.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, accumulate=True)
+    ops.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, accumulate=True, out=acc, alpha=0.5)
+    assert rel(acc, 1.5 * ref) < 2e-5
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -241,6 +245,7 @@ def test_fused_adamw_matches_reference_numerics(shadow):
         for n, p in zip(flat.names, flat.params):
             p._goat_grad.copy_(grads[n])
         flat.adamw_step(grad_scale=1.0, **opt)
+        assert float(flat.g.abs().max()) == 0.0   # zero_grad fused into the optimizer kernel
         norm, coef = O.clip_grad_norm(list(grads.values()), opt["max_grad_norm"])
         for n in ref_p:
             wd = 0.0 if any(nd in n for nd in engine.NO_DECAY) else opt["weight_decay"]
@@ -251,3 +256,19 @@ def test_fused_adamw_matches_reference_numerics(shadow):
             assert rel(p.detach(), ref_p[n]) < 1e-5, (t, n)
             if shadow is not None:
                 assert torch.equal(p._goat_shadow.cpu(), p.detach().cpu().to(shadow))
+
+
+def test_attention_ignores_stale_tmem_columns():
+    """Regression: TMEM columns beyond the score MMA's N keep whatever an earlier kernel left there (NaN after a GEMM
+    on NaN inputs); the softmax sweep must never read them (it once zeroed whole rows through a NaN row sum)."""
+    from vln_goat_b200 import ops
+    torch.manual_seed(4)
+    nan = torch.full((1024, 256), float("nan"), device=DEV, dtype=torch.bfloat16)
+    q, k, v, kmask, bias, w = (t.to(DEV) if t is not None else None
+                               for t in _attn_case(16, 12, 12, torch.bfloat16, True, seed=4))
+    ref, _ = ops.attn_fwd(q, k, v, 12, kmask, bias, force_simt=True)
+    for _ in range(3):
+        ops.gemm(nan, nan, out_dtype=torch.float32)       # poisons the accumulators' TMEM columns on every SM
+        o, _ = ops.attn_fwd(q, k, v, 12, kmask, bias)
+        assert torch.isfinite(o.float()).all()
+        assert rel(o, ref) < OUT_TOL[torch.bfloat16]

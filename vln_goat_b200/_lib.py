@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int), ("alpha", C.c_float), ("drop_p", C.c_float),
         ("drop_seed", C.c_uint64), ("drop_seed_ptr", C.c_void_p),
         ("force_simt", C.c_int),
+        ("accumulate", C.c_int),
     ]
 
 
@@ -71,7 +72,7 @@ SYMBOLS = {
     "goat_sumsq_workspace_bytes": (C.c_size_t, []),
     "goat_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "goat_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong,
-                                  C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                                  C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 _lib = None

@@ -66,6 +66,10 @@ int goat_gemm(const goat_gemm_args* a, goat_stream_t stream_) {
   ep.ldc2 = a->ldc2;
   ep.act = a->act;
   ep.out_f32 = (a->out_dtype == GOAT_F32) ? 1 : 0;
+  ep.accumulate = a->accumulate ? 1 : 0;
+  GOAT_CHECK(!a->accumulate || (a->out_dtype == GOAT_F32 && !a->bias && !a->res && !a->out2 && a->act == GOAT_ACT_NONE &&
+                                a->drop_p == 0.0f && !a->aux_out),
+             "goat_gemm: accumulate mode takes an fp32 output and no bias/res/act/dropout/out2");
   ep.alpha = a->alpha;
   ep.drop_p = a->drop_p;
   ep.drop_seed = a->drop_seed;

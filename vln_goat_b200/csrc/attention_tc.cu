@@ -33,6 +33,8 @@ constexpr int TC_THREADS = 128;
 constexpr int KC = 128;               // keys per chunk
 constexpr int TILE = 128 * 128;       // bytes of a [128 rows][64 x 2 B] tile
 constexpr int TMEM_COLS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 struct TcArgs {
   int B, heads, Nq, Nk;
@@ -108,7 +110,7 @@ struct Smem {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = 3 * TILE + 2 * TILE + 64 + 1024;  // Q K V | P(2 blocks) | barriers | alignment
+constexpr int FWD_SMEM = 3 * TILE + 2 * TILE + 64 + 512 + 1024;  // Q K V | P(2 blocks) | barriers | key mask | alignment
 
 template <typename T>
 __global__ void __launch_bounds__(TC_THREADS)
@@ -124,6 +126,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_kv = bar_q + 1;
   uint64_t* bar_mma = bar_q + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 3);
+  float* kml = reinterpret_cast<float*>(bar_q + 8);   // [128] additive key mask of the current chunk, log2 domain
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -163,11 +166,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_f16(tmem, make_smem_desc_sw128(a0 + k * 32, 0, 1024), make_smem_desc_sw128(b0 + k * 32, 0, 1024), idesc,
                k ? 1u : 0u);
   };
-  auto score = [&](float acc, int key) -> float {
-    float s = acc * p.scale;
-    if (krow) s += __ldg(krow + key);
-    if (brow) s += __ldg(brow + key);
+  const float sl2 = p.scale * LOG2E;
+  // log2-domain score of chunk-local key j (global key `key`): masked / out-of-range keys come out as -inf via kml
+  auto score = [&](float acc, int j, int key) -> float {
+    float s = fmaf(acc, sl2, kml[j]);
+    if (brow && key < p.Nk) s = fmaf(__ldg(brow + key), LOG2E, s);
     return s;
+  };
+  auto fill_kml = [&](int c) {
+    const int key = c * KC + tid;
+    kml[tid] = key < p.Nk ? (krow ? __ldg(krow + key) * LOG2E : 0.f) : -INFINITY;
   };
 
   // ---- pass A (only when the keys do not fit one chunk): exact row maxima
@@ -184,9 +192,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(bar_mma);
       }
       ph_kv ^= 1;
+      fill_kml(c);
       mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1;
       tcgen05_fence_after();
+      __syncthreads();
       if (warp_live) {
         for (int g = 0; g * 32 < nk; ++g) {
           uint32_t rr[32];
@@ -194,10 +204,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_ld_wait();
           if (rv) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int key = c * KC + g * 32 + j;
-              if (key < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), key));
-            }
+            for (int j = 0; j < 32; ++j)
+              if (c * KC + g * 32 + j < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), g * 32 + j, c * KC + g * 32 + j));
           }
         }
       }
@@ -220,9 +228,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(bar_mma);
     }
     ph_kv ^= 1;
+    fill_kml(c);
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tcgen05_fence_after();
+    __syncthreads();
     if (warp_live) {
       if (nchunks == 1) {
         for (int g = 0; g * 32 < nk; ++g) {
@@ -231,10 +241,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_ld_wait();
           if (rv) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int key = g * 32 + j;
-              if (key < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), key));
-            }
+            for (int j = 0; j < 32; ++j)
+              if (g * 32 + j < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), g * 32 + j, g * 32 + j));
           }
         }
       }
@@ -248,8 +256,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int j = 0; j < 32; ++j) {
           const int key = c * KC + g * 32 + j;
           float e = 0.f;
-          if (rv && key < p.Nk) {
-            e = __expf(score(__uint_as_float(rr[j]), key) - mref);
+          if (rv && key < p.Nk) {   // TMEM columns past the MMA's N hold stale data (possibly NaN): never touch them
+            e = ex2_approx(score(__uint_as_float(rr[j]), g * 32 + j, key) - mref);
             l += e;
             if (p.drop_p > 0.f) e *= drop_mul(p, seed, b, h, r, key);
           }
@@ -290,7 +298,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float inv = l > 0.f ? 1.f / l : 0.f;
       T* dst = reinterpret_cast<T*>(p.O) + (long long)b * p.sbo + (long long)r * p.ldo + h * 64;
       store_global_row64<T>(dst, o, inv);
-      if (p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + r] = l > 0.f ? m + __logf(l) : -INFINITY;
+      if (p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + r] = l > 0.f ? (m + __log2f(l)) * LN2 : -INFINITY;
     }
   }
   tcgen05_fence_before();
@@ -301,7 +309,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = 4 * TILE + 4 * TILE + 64 + 1024;  // Q dO K V | P(2) dS(2) | barriers | alignment
+constexpr int BWD_SMEM = 4 * TILE + 4 * TILE + 64 + 512 + 1024;  // Q dO K V | P(2) dS(2) | barriers | key mask | alignment
 
 template <typename T>
 __global__ void __launch_bounds__(TC_THREADS)
@@ -319,6 +327,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_kv = bar_q + 1;
   uint64_t* bar_mma = bar_q + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 3);
+  float* kml = reinterpret_cast<float*>(bar_q + 8);   // [128] additive key mask of the current chunk, log2 domain
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -364,8 +373,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       x = unpack2<T>(a.z); y = unpack2<T>(g.z); delta += x.x * y.x + x.y * y.y;
       x = unpack2<T>(a.w); y = unpack2<T>(g.w); delta += x.x * y.x + x.y * y.y;
     }
-    lse = p.lse[((long long)b * p.heads + h) * p.Nq + r];
+    lse = p.lse[((long long)b * p.heads + h) * p.Nq + r] * LOG2E;
   }
+  const float sl2 = p.scale * LOG2E;
   float dq[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) dq[j] = 0.f;
@@ -393,9 +403,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(bar_mma);
     }
     ph_kv ^= 1;
+    {
+      const int key = c * KC + tid;
+      kml[tid] = key < p.Nk ? (krow ? __ldg(krow + key) * LOG2E : 0.f) : -INFINITY;
+    }
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tcgen05_fence_after();
+    __syncthreads();
 
     for (int g = 0; g * 32 < nk16; ++g) {
       uint32_t rs[32], rp[32];
@@ -408,10 +423,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int key = c * KC + g * 32 + j;
         float pd = 0.f, ds = 0.f;
         if (rv && key < p.Nk) {
-          float s = __uint_as_float(rs[j]) * p.scale;
-          if (krow) s += __ldg(krow + key);
-          if (brow) s += __ldg(brow + key);
-          const float pr = __expf(s - lse);
+          float s = fmaf(__uint_as_float(rs[j]), sl2, kml[g * 32 + j]);
+          if (brow) s = fmaf(__ldg(brow + key), LOG2E, s);
+          const float pr = ex2_approx(s - lse);
           const float dm = p.drop_p > 0.f ? drop_mul(p, seed, b, h, r, key) : 1.f;
           pd = pr * dm;
           ds = pr * (__uint_as_float(rp[j]) * dm - delta);

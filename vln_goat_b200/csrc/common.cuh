@@ -100,14 +100,46 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// counter-based uniform in [0,1): splitmix64 over (seed, index). Used for dropout masks so the
-// backward pass can regenerate the forward mask from (seed, element index) without storing it.
+// counter-based uniform in [0,1): a 32-bit multiply-xorshift hash of (seed, index).  Used for dropout masks so
+// the backward pass can regenerate the forward mask from (seed, element index) without storing it.  Seven integer
+// instructions per element (the 64-bit splitmix this replaced cost ~4x that in the GEMM / attention epilogues);
+// statistical quality is ample for Bernoulli masks (tests check the keep rate and mask equality across kernels).
 __device__ __forceinline__ float rand_uniform(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(unsigned int)(z >> 40) * (1.0f / 16777216.0f);
+  unsigned int x = (unsigned int)idx * 0x9E3779B1u + (unsigned int)seed;
+  x ^= (unsigned int)(idx >> 32) * 0x85EBCA6Bu + (unsigned int)(seed >> 32);
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+// erf-GELU and its derivative for the 16-bit tensor-core epilogues: Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7,
+// far below fp16 / bf16 output rounding) with one MUFU.RCP and one MUFU.EX2; exp(-x^2/2) is shared between the
+// erf tail and the Gaussian density of the derivative.  The fp32 parity path keeps erff (gelu_erf / dgelu_erf).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  e = ex2_approx(-u * u * 1.4426950408889634f);          // exp(-x^2 / 2)
+  const float erf_abs = 1.0f - poly * e;
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return cdf + x * e * 0.39894228040143267794f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -123,6 +155,7 @@ struct EpiParams {
   int ldc, ldres, ldaux, ldc2;
   int act;               // goat_act_t
   int out_f32;           // 1: out is fp32, 0: out is T
+  int accumulate;        // 1: out (fp32) += alpha * acc with atomics, no other epilogue term (split-K wgrad)
   float alpha;           // scales the accumulator before bias
   float drop_p;          // dropout probability applied after activation, before residual (0 = off)
   unsigned long long drop_seed;

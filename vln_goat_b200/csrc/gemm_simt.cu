@@ -67,6 +67,10 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, EpiParams ep,
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
+      if (ep.accumulate) {
+        atomicAdd(reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldc + n, acc[i][j] * ep.alpha);
+        continue;
+      }
       const float v = epi_apply<T>(ep, m, n, acc[i][j]);
       if (ep.out_f32) reinterpret_cast<float*>(ep.out)[(size_t)m * ep.ldc + n] = v;
       else reinterpret_cast<T*>(ep.out)[(size_t)m * ep.ldc + n] = from_f<T>(v);

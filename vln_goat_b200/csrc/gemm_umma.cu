@@ -1,11 +1,16 @@
 // tcgen05 GEMM for sm_100a: out[M,N] = epilogue(A[M,K] * B[N,K]^T), fp16/bf16 operands, fp32 accumulation.
 //
-// One CTA computes one 128 x BLOCK_N output tile.  Warp roles (192 threads):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor tiles of A and B into a STAGES-deep smem ring
-//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16),
-//              accumulator lives in TMEM; tcgen05.commit releases smem stages / signals the epilogue
-//   warps 2-5: epilogue -- tcgen05.ld the accumulator (each warp owns TMEM lanes 32*(warp%4)..+31),
-//              bias / GELU / dGELU / dropout / residual, vectorised stores
+// Persistent, warp-specialised: each CTA (one per SM) walks a static list of 128 x 128 output tiles
+// (tile = blockIdx.x + i * gridDim.x; N fastest so concurrently running CTAs share A panels in L2).
+//   warp 0    : TMA producer  -- cp.async.bulk.tensor tiles of A and B into a STAGES-deep smem ring
+//   warp 1    : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma (UMMA 128 x 128 x 16) into one
+//               of TWO TMEM accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2-9 : epilogue -- warp w owns TMEM lanes 32*(w%4).. and one column half; tcgen05.ld 32 columns, transpose
+//               through a private padded smem patch so that every global access (bias / residual / GELU aux /
+//               output) is a coalesced 16-byte access along the row, then bias / GELU / dGELU / dropout / residual
+// Split-K (accumulate mode, wgrad): the K range is cut into `splits` tile-sized pieces that are scheduled as
+// independent tiles and reduced with vector fp32 atomics (red.global.add.v4.f32) into a zero-initialised output --
+// a 768 x 768 x 5120 weight-gradient GEMM has only 36 output tiles for 148 SMs otherwise.
 // Operands may be K-major (contraction dim contiguous: activations and weights in forward) or
 // MN-major (dY and W in dgrad, dY and X in wgrad); both use the SWIZZLE_128B canonical layouts, the
 // major-ness goes into the instruction descriptor and the smem matrix descriptors.
@@ -21,34 +26,133 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int PATCH_LD = 36;                       // floats per staged row (32 + 4 padding: conflict-free both ways)
+constexpr int PATCH_BYTES = 32 * PATCH_LD * 4;     // one warp's 32 x 32 transpose patch
 
 template <int BLOCK_N, int STAGES>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * PATCH_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
+
+struct Sched {
+  int tiles_m, tiles_n, splits, kb_per_split, num_kb, num_tiles;
+};
+
+__device__ __forceinline__ void tile_coords(const Sched& sc, int t, int& m0, int& n0, int& kb0, int& kb1) {
+  const int tn = t % sc.tiles_n;
+  const int r = t / sc.tiles_n;
+  const int tm = r % sc.tiles_m;
+  const int ks = r / sc.tiles_m;
+  m0 = tm * BLOCK_M;
+  n0 = tn * 128;
+  kb0 = ks * sc.kb_per_split;
+  kb1 = min(sc.num_kb, kb0 + sc.kb_per_split);
+}
+
+// 4 consecutive outputs (row m, columns n..n+3) through the fused epilogue, vector global accesses
+template <typename T>
+__device__ __forceinline__ void epi_store4(const EpiParams& ep, int m, int n, float4 acc, unsigned long long seed) {
+  float v[4] = {acc.x * ep.alpha, acc.y * ep.alpha, acc.z * ep.alpha, acc.w * ep.alpha};
+  if (ep.accumulate) {
+    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldc + n),
+              make_float4(v[0], v[1], v[2], v[3]));
+    return;
+  }
+  if (ep.bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.act == GOAT_ACT_GELU) {
+    if (ep.aux_out) {
+      uint2 w;
+      w.x = pack2<T>(v[0], v[1]);
+      w.y = pack2<T>(v[2], v[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<T*>(ep.aux_out) + (size_t)m * ep.ldaux + n) = w;
+      // GELU of the ROUNDED pre-activation: backward only ever sees the stored 16-bit z
+      float2 f;
+      f = unpack2<T>(w.x); v[0] = f.x; v[1] = f.y;
+      f = unpack2<T>(w.y); v[2] = f.x; v[3] = f.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
+  } else if (ep.act == GOAT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (ep.act == GOAT_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = tanhf(v[j]);
+  } else if (ep.act == GOAT_ACT_DGELU || ep.act == GOAT_ACT_DRELU) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(ep.aux_in) + (size_t)m * ep.ldaux + n));
+    const float2 a = unpack2<T>(w.x), b = unpack2<T>(w.y);
+    const float z[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      v[j] = (ep.act == GOAT_ACT_DGELU) ? v[j] * dgelu_fast(z[j]) : (z[j] > 0.0f ? v[j] : 0.0f);
+  }
+  if (ep.drop_p > 0.0f) {
+    const float keep = 1.0f / (1.0f - ep.drop_p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float u = rand_uniform(seed, (unsigned long long)m * (unsigned long long)ep.ldc + n + j);
+      v[j] = (u >= ep.drop_p) ? v[j] * keep : 0.0f;
+    }
+  }
+  if (ep.res) {
+    const float4 b = *reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.ldres + n);
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.out_f32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint2 w;
+    w.x = pack2<T>(v[0], v[1]);
+    w.y = pack2<T>(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<T*>(ep.out) + (size_t)m * ep.ldc + n) = w;
+  }
+  if (ep.out2) {
+    uint2 w;
+    w.x = pack2<T>(v[0], v[1]);
+    w.y = pack2<T>(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<T*>(ep.out2) + (size_t)m * ep.ldc2 + n) = w;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void epi_store1(const EpiParams& ep, int m, int n, float acc) {
+  if (ep.accumulate) {
+    atomicAdd(reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldc + n, acc * ep.alpha);
+    return;
+  }
+  const float val = epi_apply<T>(ep, m, n, acc);
+  if (ep.out_f32) reinterpret_cast<float*>(ep.out)[(size_t)m * ep.ldc + n] = val;
+  else reinterpret_cast<T*>(ep.out)[(size_t)m * ep.ldc + n] = from_f<T>(val);
+  if (ep.out2) reinterpret_cast<T*>(ep.out2)[(size_t)m * ep.ldc2 + n] = from_f<T>(val);
+}
 
 template <typename T, int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep,
-                 int M, int N, int K) {
+                 int M, int N, int K, Sched sc) {
+  static_assert(BLOCK_N == 128, "tile scheduler and TMEM double buffering assume 128-wide tiles");
   using C = Cfg<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  float* patches = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
-  const int m0 = blockIdx.y * BLOCK_M;
-  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -58,10 +162,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -69,183 +177,130 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        uint8_t* sa = smem + s * C::STAGE_BYTES;
-        uint8_t* sb = sa + C::A_BYTES;
-        const int k0 = kb * BLOCK_K;
-        if (!A_MN) {
-          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 m}
-        } else {
+      uint32_t it = 0;  // running k-block counter across tiles: stage = it % STAGES
+      for (int t = blockIdx.x; t < sc.num_tiles; t += gridDim.x) {
+        int m0, n0, kb0, kb1;
+        tile_coords(sc, t, m0, n0, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 m}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_M / 64; ++j)       // boxes {64 m, 64 k}
-            tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, k0);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BLOCK_N n}
-        } else {
+            for (int j = 0; j < BLOCK_M / 64; ++j)       // boxes {64 m, 64 k}
+              tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BLOCK_N n}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(UmmaFmt<T>::value, A_MN ? 1 : 0, B_MN ? 1 : 0, BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < sc.num_tiles; t += gridDim.x, ++local) {
+        int m0, n0, kb0, kb1;
+        tile_coords(sc, t, m0, n0, kb0, kb1);
+        const int buf = local & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)local >> 1) & 1) ^ 1);   // epilogue drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t sb = sa + C::A_BYTES;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // K-major : 8-row groups 1024 B apart (SBO); advance 16 elements = 32 B inside the swizzle row.
-          // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
-          //           advance 16 k-rows = 2048 B.
-          const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                   : make_smem_desc_sw128(sa + k * 32, 0, 1024);
-          const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                   : make_smem_desc_sw128(sb + k * 32, 0, 1024);
-          umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major : 8-row groups 1024 B apart (SBO); advance 16 elements = 32 B inside the swizzle row.
+            // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+            //           advance 16 k-rows = 2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_f16(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
+        umma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int lg = warp & 3;  // TMEM lane group this warp may access
-    const int row = m0 + lg * 32 + lane;
-    const bool row_ok = row < M;
-    const bool vec_ok = ((ep.ldc & 7) == 0) && (!ep.res || (ep.ldres & 3) == 0) && ((ep.ldaux & 7) == 0) &&
-                        (!ep.out2 || (ep.ldc2 & 7) == 0);
+    const int ew = warp - 2;
+    const int lg = warp & 3;          // TMEM lane group this warp may access
+    const int chalf = ew >> 2;        // which 64-column half of the tile
+    float* patch = patches + ew * (PATCH_BYTES / 4);
+    const unsigned long long seed = ep.drop_p > 0.0f ? eff_seed(ep.drop_seed, ep.drop_seed_ptr) : 0ull;
+    const bool vec_ok = ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldres & 3) == 0) &&
+                        ((!ep.aux_in && !ep.aux_out) || (ep.ldaux & 3) == 0) && (!ep.out2 || (ep.ldc2 & 3) == 0);
+    const int rl = lane >> 3;         // row within a group of 4
+    const int c4 = (lane & 7) * 4;    // column offset of this lane's float4
+    int local = 0;
+    for (int t = blockIdx.x; t < sc.num_tiles; t += gridDim.x, ++local) {
+      int m0, n0, kb0, kb1;
+      tile_coords(sc, t, m0, n0, kb0, kb1);
+      const int buf = local & 1;
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)local >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BLOCK_N) + ((uint32_t)(lg * 32) << 16);
+      const bool has_k = kb1 > kb0;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      const int nc = n0 + c * 32;
-      if (!row_ok || nc >= N) continue;
-      if (vec_ok && nc + 32 <= N) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
+      for (int c = 0; c < 2; ++c) {
+        const int cbase = chalf * 64 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tacc + (uint32_t)cbase, r);
+        tmem_ld_wait();
+        if (c == 1) {
+          // every TMEM read of this warp for this tile is done: hand the accumulator back to the MMA warp
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
-        if (ep.act == GOAT_ACT_GELU) {
-          if (ep.aux_out) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(ep.aux_out) + (size_t)row * ep.ldaux + nc);
+        const int nc = n0 + cbase;
+        if (nc >= N || m0 + lg * 32 >= M || !has_k) continue;   // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              w.x = pack2<T>(v[j], v[j + 1]); w.y = pack2<T>(v[j + 2], v[j + 3]);
-              w.z = pack2<T>(v[j + 4], v[j + 5]); w.w = pack2<T>(v[j + 6], v[j + 7]);
-              dst[j >> 3] = w;
-              float2 f;
-              f = unpack2<T>(w.x); v[j] = f.x; v[j + 1] = f.y;
-              f = unpack2<T>(w.y); v[j + 2] = f.x; v[j + 3] = f.y;
-              f = unpack2<T>(w.z); v[j + 4] = f.x; v[j + 5] = f.y;
-              f = unpack2<T>(w.w); v[j + 6] = f.x; v[j + 7] = f.y;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(patch + lane * PATCH_LD + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int row_l = i * 4 + rl;
+          const int m = m0 + lg * 32 + row_l;
+          const int n = nc + c4;
+          if (m < M && n < N) {
+            const float4 acc = *reinterpret_cast<const float4*>(patch + row_l * PATCH_LD + c4);
+            if (vec_ok && n + 4 <= N) {
+              epi_store4<T>(ep, m, n, acc, seed);
+            } else {
+              const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+              for (int j = 0; j < 4 && n + j < N; ++j) epi_store1<T>(ep, m, n + j, a4[j]);
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (ep.act == GOAT_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        } else if (ep.act == GOAT_ACT_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-        } else if (ep.act == GOAT_ACT_DGELU || ep.act == GOAT_ACT_DRELU) {
-          const uint4* src =
-              reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(ep.aux_in) + (size_t)row * ep.ldaux + nc);
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 w = __ldg(src + (j >> 3));
-            float z[8];
-            float2 f;
-            f = unpack2<T>(w.x); z[0] = f.x; z[1] = f.y;
-            f = unpack2<T>(w.y); z[2] = f.x; z[3] = f.y;
-            f = unpack2<T>(w.z); z[4] = f.x; z[5] = f.y;
-            f = unpack2<T>(w.w); z[6] = f.x; z[7] = f.y;
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-              v[j + t] = (ep.act == GOAT_ACT_DGELU) ? v[j + t] * dgelu_erf(z[t]) : (z[t] > 0.0f ? v[j + t] : 0.0f);
-          }
         }
-        if (ep.drop_p > 0.0f) {
-          const float keep = 1.0f / (1.0f - ep.drop_p);
-          const unsigned long long seed = eff_seed(ep.drop_seed, ep.drop_seed_ptr);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float u = rand_uniform(seed, (unsigned long long)row * (unsigned long long)ep.ldc + nc + j);
-            v[j] = (u >= ep.drop_p) ? v[j] * keep : 0.0f;
-          }
-        }
-        if (ep.res) {
-          const float4* src = reinterpret_cast<const float4*>(ep.res + (size_t)row * ep.ldres + nc);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = src[j >> 2];
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (ep.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + nc);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(ep.out) + (size_t)row * ep.ldc + nc);
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 w;
-            w.x = pack2<T>(v[j], v[j + 1]); w.y = pack2<T>(v[j + 2], v[j + 3]);
-            w.z = pack2<T>(v[j + 4], v[j + 5]); w.w = pack2<T>(v[j + 6], v[j + 7]);
-            dst[j >> 3] = w;
-          }
-        }
-        if (ep.out2) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(ep.out2) + (size_t)row * ep.ldc2 + nc);
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 w;
-            w.x = pack2<T>(v[j], v[j + 1]); w.y = pack2<T>(v[j + 2], v[j + 3]);
-            w.z = pack2<T>(v[j + 4], v[j + 5]); w.w = pack2<T>(v[j + 6], v[j + 7]);
-            dst[j >> 3] = w;
-          }
-        }
-      } else {
-        // ragged / unaligned edge: scalar path through the shared epilogue
-        EpiParams e1 = ep;
-        e1.alpha = ep.alpha;
-#pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
-          const int n = nc + j;
-          if (n >= N) break;
-          const float val = epi_apply<T>(e1, row, n, __uint_as_float(r[j]));
-          if (ep.out_f32) reinterpret_cast<float*>(ep.out)[(size_t)row * ep.ldc + n] = val;
-          else reinterpret_cast<T*>(ep.out)[(size_t)row * ep.ldc + n] = from_f<T>(val);
-          if (ep.out2) reinterpret_cast<T*>(ep.out2)[(size_t)row * ep.ldc2 + n] = from_f<T>(val);
-        }
+        __syncwarp();
       }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+  if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,6 +362,16 @@ int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64
 
 namespace {
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <typename T, int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, STAGES>;
@@ -324,18 +389,34 @@ int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   if (!B_MN) rc = make_tmap(&tmB, a.dtype, a.B, a.K, a.N, a.ldb, BLOCK_K, BLOCK_N);
   else rc = make_tmap(&tmB, a.dtype, a.B, a.N, a.K, a.ldb, 64, BLOCK_K);
   if (rc) return rc;
-  dim3 grid((a.N + BLOCK_N - 1) / BLOCK_N, (a.M + BLOCK_M - 1) / BLOCK_M);
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, a.M, a.N, a.K);
+  Sched sc;
+  sc.tiles_m = (a.M + BLOCK_M - 1) / BLOCK_M;
+  sc.tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
+  sc.num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+  sc.splits = 1;
+  const int mn = sc.tiles_m * sc.tiles_n;
+  if (ep.accumulate && mn < num_sms()) {
+    // split K so that about one wave of tiles exists, keeping at least 4 k-blocks (256 of K) per split
+    int want = (num_sms() + mn - 1) / mn;
+    int cap = sc.num_kb / 4;
+    if (cap < 1) cap = 1;
+    sc.splits = want < cap ? want : cap;
+  }
+  sc.kb_per_split = (sc.num_kb + sc.splits - 1) / sc.splits;
+  sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
+  sc.num_tiles = mn * sc.splits;
+  const int grid = sc.num_tiles < num_sms() ? sc.num_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, a.M, a.N, a.K, sc);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
 
 template <typename T>
 int dispatch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
-  if (!a.a_mn_major && !a.b_mn_major) return launch<T, 128, 6, false, false>(a, ep, stream);
-  if (!a.a_mn_major && a.b_mn_major) return launch<T, 128, 6, false, true>(a, ep, stream);
-  if (a.a_mn_major && a.b_mn_major) return launch<T, 128, 6, true, true>(a, ep, stream);
-  return launch<T, 128, 6, true, false>(a, ep, stream);
+  if (!a.a_mn_major && !a.b_mn_major) return launch<T, 128, 5, false, false>(a, ep, stream);
+  if (!a.a_mn_major && a.b_mn_major) return launch<T, 128, 5, false, true>(a, ep, stream);
+  if (a.a_mn_major && a.b_mn_major) return launch<T, 128, 5, true, true>(a, ep, stream);
+  return launch<T, 128, 5, true, false>(a, ep, stream);
 }
 
 }  // namespace

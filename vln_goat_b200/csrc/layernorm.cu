@@ -157,6 +157,195 @@ __global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int np
   if (dcolsum) dcolsum[c] = d;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised variants for H = 128 * NV (768 -> NV = 6): one warp per row, lane owns float4 columns
+// c = i*128 + lane*4, i < NV.  All global accesses are 16-byte (8-byte for 16-bit outputs), the row stays in
+// registers between the statistics and the normalisation pass.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float4 ld4(const void* p, size_t i) {
+  if constexpr (sizeof(T) == 4) {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+  } else {
+    const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p) + i);
+    const float2 a = unpack2<T>(w.x), b = unpack2<T>(w.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st4(void* p, size_t i, float4 v) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v;
+  } else {
+    uint2 w;
+    w.x = pack2<T>(v.x, v.y);
+    w.y = pack2<T>(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<T*>(p) + i) = w;
+  }
+}
+
+template <typename TX, typename TY, int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_vec_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                  float* __restrict__ y32, void* __restrict__ y16, float* __restrict__ mean, float* __restrict__ rstd,
+                  int M) {
+  constexpr int H = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = ld4<TX>(x, (size_t)row * H + i * 128 + lane * 4);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mu = warp_sum(s) * (1.f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rs = rsqrtf(warp_sum(q) * (1.f / H) + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y;
+    y.x = (v[i].x - mu) * rs * g.x + b.x;
+    y.y = (v[i].y - mu) * rs * g.y + b.y;
+    y.z = (v[i].z - mu) * rs * g.z + b.z;
+    y.w = (v[i].w - mu) * rs * g.w + b.w;
+    if (y32) st4<float>(y32, (size_t)row * H + c, y);
+    if (y16) st4<TY>(y16, (size_t)row * H + c, y);
+  }
+}
+
+template <typename TX, typename TD, int NV>
+__global__ void __launch_bounds__(128)
+ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+                  float* __restrict__ dx32, void* __restrict__ dx16, float drop_p, unsigned long long drop_seed_,
+                  const unsigned long long* __restrict__ drop_seed_ptr, float* __restrict__ partial, int M,
+                  int rows_per_cta) {
+  constexpr int H = NV * 128;
+  extern __shared__ float sacc[];  // [4 warps][3][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 ag[NV], ab[NV], ac[NV], gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
+  }
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  const float keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const unsigned long long drop_seed = drop_p > 0.f ? eff_seed(drop_seed_, drop_seed_ptr) : 0ull;
+  for (int row = r0 + warp; row < r1; row += 4) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const size_t o = (size_t)row * H + i * 128 + lane * 4;
+      const float4 d = *reinterpret_cast<const float4*>(dy + o);
+      const float4 xv = ld4<TX>(x, o);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+      s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+    }
+    s1 = warp_sum(s1) * (1.f / H);
+    s2 = warp_sum(s2) * (1.f / H);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 128 + lane * 4;
+      const size_t o = (size_t)row * H + c;
+      float4 d;
+      d.x = rs * (g[i].x - s1 - xh[i].x * s2);
+      d.y = rs * (g[i].y - s1 - xh[i].y * s2);
+      d.z = rs * (g[i].z - s1 - xh[i].z * s2);
+      d.w = rs * (g[i].w - s1 - xh[i].w * s2);
+      if (dx32) {
+        float4 w = d;
+        if (dres) {
+          const float4 rr = *reinterpret_cast<const float4*>(dres + o);
+          w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(dx32 + o) = w;
+      }
+      float4 dm = d;
+      if (drop_p > 0.f) {
+        dm.x = rand_uniform(drop_seed, (unsigned long long)o + 0) >= drop_p ? d.x * keep : 0.f;
+        dm.y = rand_uniform(drop_seed, (unsigned long long)o + 1) >= drop_p ? d.y * keep : 0.f;
+        dm.z = rand_uniform(drop_seed, (unsigned long long)o + 2) >= drop_p ? d.z * keep : 0.f;
+        dm.w = rand_uniform(drop_seed, (unsigned long long)o + 3) >= drop_p ? d.w * keep : 0.f;
+      }
+      if (dx16) {
+        st4<TD>(dx16, o, dm);
+        if constexpr (sizeof(TD) == 2) {   // the column sum must see the rounded values the GEMMs will read
+          dm.x = to_f<TD>(from_f<TD>(dm.x)); dm.y = to_f<TD>(from_f<TD>(dm.y));
+          dm.z = to_f<TD>(from_f<TD>(dm.z)); dm.w = to_f<TD>(from_f<TD>(dm.w));
+        }
+      }
+      ac[i].x += dm.x; ac[i].y += dm.y; ac[i].z += dm.z; ac[i].w += dm.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    *reinterpret_cast<float4*>(&sacc[(warp * 3 + 0) * H + c]) = ag[i];
+    *reinterpret_cast<float4*>(&sacc[(warp * 3 + 1) * H + c]) = ab[i];
+    *reinterpret_cast<float4*>(&sacc[(warp * 3 + 2) * H + c]) = ac[i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) t += sacc[w * 3 * H + e];
+    partial[(size_t)blockIdx.x * 3 * H + e] = t;
+  }
+}
+
+// partial [nparts][3][H] -> dgamma / dbeta / dcolsum; block (32 columns, 8 part-groups), grid (H/32, 3)
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_vec_kernel(const float* __restrict__ partial, int nparts, int H, float* dgamma, float* dbeta,
+                           float* dcolsum) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.y;
+  float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dcolsum);
+  if (!out) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float t = 0.f;
+  if (c < H)
+    for (int p = ty; p < nparts; p += 8) t += partial[((size_t)p * 3 + k) * H + c];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < H) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][tx];
+    out[c] = a;
+  }
+}
+
+inline int ln_bwd_vec_parts(int M) {
+  int parts = (M + 15) / 16;      // >= 16 rows per CTA (2 per warp)
+  if (parts > 296) parts = 296;   // 2 CTAs per SM on 148 SMs
+  if (parts < 1) parts = 1;
+  return parts;
+}
+
 inline int ln_bwd_parts(int M) {
   int parts = (M + 31) / 32;   // >= 32 rows per CTA
   if (parts > 592) parts = 592;  // 4 CTAs per SM on 148 SMs
@@ -236,6 +425,18 @@ extern "C" int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma
   GOAT_CHECK(!y16 || y16_dtype == GOAT_F16 || y16_dtype == GOAT_BF16, "goat_layernorm_fwd: y16 dtype must be F16/BF16");
   if (M <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (H == 768 && aligned16(x) && (!y32 || aligned16(y32)) && (!y16 || aligned16(y16)) && aligned16(gamma) && aligned16(beta)) {
+    dim3 g8((M + 7) / 8);
+#define LN_FWDV(TX, TY) ln_fwd_vec_kernel<TX, TY, 6><<<g8, 256, 0, st>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M)
+    const bool yh8 = (y16_dtype == GOAT_F16);
+    if (x_dtype == GOAT_F32) { if (yh8) LN_FWDV(float, __half); else LN_FWDV(float, __nv_bfloat16); }
+    else if (x_dtype == GOAT_F16) { if (yh8) LN_FWDV(__half, __half); else LN_FWDV(__half, __nv_bfloat16); }
+    else if (x_dtype == GOAT_BF16) { if (yh8) LN_FWDV(__nv_bfloat16, __half); else LN_FWDV(__nv_bfloat16, __nv_bfloat16); }
+    else GOAT_CHECK(false, "goat_layernorm_fwd: bad x dtype");
+#undef LN_FWDV
+    GOAT_LAUNCH_CHECK();
+    return GOAT_OK;
+  }
   dim3 grid((M + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA);
 #define LN_FWD(TX, TY) ln_fwd_kernel<TX, TY><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M, H)
   const bool yh = (y16_dtype == GOAT_F16);
@@ -249,7 +450,8 @@ extern "C" int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma
 }
 
 extern "C" size_t goat_layernorm_bwd_workspace_bytes(int M, int H) {
-  return (size_t)ln_bwd_parts(M) * 3 * (size_t)H * sizeof(float);
+  const int parts = ln_bwd_parts(M) > ln_bwd_vec_parts(M) ? ln_bwd_parts(M) : ln_bwd_vec_parts(M);
+  return (size_t)parts * 3 * (size_t)H * sizeof(float);
 }
 
 extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
@@ -263,10 +465,43 @@ extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, c
   GOAT_CHECK(drop_p >= 0.f && drop_p < 1.f, "goat_layernorm_bwd: drop_p out of range");
   if (M <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* partial = reinterpret_cast<float*>(workspace);
+  if (H == 768 && aligned16(dy) && aligned16(x) && aligned16(gamma) && (!dres || aligned16(dres)) &&
+      (!dx32 || aligned16(dx32)) && (!dx16 || aligned16(dx16))) {
+    const int vparts = ln_bwd_vec_parts(M);
+    const int vrows = (M + vparts - 1) / vparts;
+    constexpr int VSMEM = 4 * 3 * 768 * 4;
+    const int ddv = dx16 ? dx16_dtype : GOAT_F16;
+#define LN_BWDV(TX, TD)                                                                                               \
+  do {                                                                                                                \
+    static bool cfgv = false;                                                                                         \
+    if (!cfgv) {                                                                                                      \
+      GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_vec_kernel<TX, TD, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, VSMEM)); \
+      cfgv = true;                                                                                                    \
+    }                                                                                                                 \
+    ln_bwd_vec_kernel<TX, TD, 6><<<vparts, 128, VSMEM, st>>>(dy, x, gamma, mean, rstd, dres, dx32, dx16, drop_p,      \
+        drop_seed, reinterpret_cast<const unsigned long long*>(drop_seed_ptr), partial, M, vrows);                    \
+  } while (0)
+#define LN_BWDV_X(TX)                                                     \
+  do {                                                                    \
+    if (ddv == GOAT_F16) LN_BWDV(TX, __half);                             \
+    else if (ddv == GOAT_BF16) LN_BWDV(TX, __nv_bfloat16);                \
+    else LN_BWDV(TX, float);                                              \
+  } while (0)
+    if (x_dtype == GOAT_F32) LN_BWDV_X(float);
+    else if (x_dtype == GOAT_F16) LN_BWDV_X(__half);
+    else if (x_dtype == GOAT_BF16) LN_BWDV_X(__nv_bfloat16);
+    else GOAT_CHECK(false, "goat_layernorm_bwd: bad x dtype");
+#undef LN_BWDV_X
+#undef LN_BWDV
+    GOAT_LAUNCH_CHECK();
+    ln_bwd_finalize_vec_kernel<<<dim3(768 / 32, 3), 256, 0, st>>>(partial, vparts, H, dgamma, dbeta, dcolsum);
+    GOAT_LAUNCH_CHECK();
+    return GOAT_OK;
+  }
   const int parts = ln_bwd_parts(M);
   const int rows_per_cta = (M + parts - 1) / parts;
   const size_t smem = (size_t)4 * 3 * H * sizeof(float);
-  float* partial = reinterpret_cast<float*>(workspace);
 #define LN_BWD(TX, TD)                                                                                                \
   do {                                                                                                                \
     static bool cfg = false;                                                                                          \

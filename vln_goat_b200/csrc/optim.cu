@@ -5,7 +5,7 @@
 //   goat_sumsq      partial[g] = sum of squares of a grid-strided slice of the flat gradient
 //   goat_adamw_step every CTA reduces partial[] in a fixed order (deterministic) -> clip coefficient,
 //                   then updates p, m, v in place and writes the bf16/fp16 copy the GEMMs read next step.
-// HBM-bound: 16 B read + 14 B written per parameter.  Hyper-parameters live in a small DEVICE array so a
+// HBM-bound: 16 B read + 18 B written per parameter (p, m, v, the 16-bit shadow and the cleared gradient).  Hyper-parameters live in a small DEVICE array so a
 // captured CUDA graph can be replayed with a new learning rate / bias correction each step.
 #include "common.cuh"
 
@@ -42,9 +42,9 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(const float* __restr
 //                    [7] max_grad_norm (<= 0: no clipping)  [8] gradient pre-scale (1/world for summed grads)
 template <typename TS>
 __global__ void __launch_bounds__(OPT_THREADS)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              TS* __restrict__ shadow, long long n, long long n_decay, const float* __restrict__ hp,
-             const float* __restrict__ partial, int nparts, float* __restrict__ norm_out) {
+             const float* __restrict__ partial, int nparts, float* __restrict__ norm_out, int zero_grad) {
   __shared__ float s_coef;
   if (threadIdx.x < 32) {
     float t = 0.f;
@@ -85,6 +85,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (shadow) {
       if constexpr (sizeof(TS) == 2) {
         uint2 w;
@@ -102,6 +103,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       float x = p[i] - step_size * (mi / (sqrtf(vi) + eps));
       if (i < n_decay) x -= x * (lr * wd);
       p[i] = x; m[i] = mi; v[i] = vi;
+      if (zero_grad) g[i] = 0.f;
       if (shadow) { if constexpr (sizeof(TS) == 2) shadow[i] = from_f<TS>(x); }
     }
   }
@@ -125,9 +127,9 @@ extern "C" int goat_sumsq(const float* g, long long n, float* partial, int* npar
   return GOAT_OK;
 }
 
-extern "C" int goat_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
+extern "C" int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
                                long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
-                               goat_stream_t stream) {
+                               int zero_grad, goat_stream_t stream) {
   GOAT_CHECK(p && g && m && v && hp && partial, "goat_adamw_step: null argument");
   GOAT_CHECK(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || aligned16(shadow)),
              "goat_adamw_step: buffers must be 16-byte aligned");
@@ -138,11 +140,11 @@ extern "C" int goat_adamw_step(float* p, const float* g, float* m, float* v, voi
   long long want = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   const int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
   if (shadow && shadow_dtype == GOAT_F16)
-    adamw_kernel<__half><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__half*)shadow, n, n_decay, hp, partial, nparts, norm_out);
+    adamw_kernel<__half><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__half*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad);
   else if (shadow)
-    adamw_kernel<__nv_bfloat16><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, n_decay, hp, partial, nparts, norm_out);
+    adamw_kernel<__nv_bfloat16><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad);
   else
-    adamw_kernel<float><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (float*)nullptr, n, n_decay, hp, partial, nparts, norm_out);
+    adamw_kernel<float><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (float*)nullptr, n, n_decay, hp, partial, nparts, norm_out, zero_grad);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

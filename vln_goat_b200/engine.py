@@ -94,8 +94,9 @@ class FlatParams(object):
             ops.cast(self.p, self.shadow_dtype, out=self.shadow)
 
     def begin_step(self):
-        """Mark every gradient view as unwritten: the first backward write of the step overwrites, later ones
-        (a parameter used twice) accumulate.  No memset of the gradient buffer is needed."""
+        """Mark every gradient view as unwritten.  Vector gradients (biases, LayerNorm) overwrite on their first
+        write of a step and add afterwards; weight gradients always accumulate (split-K atomics) into the buffer
+        that ``adamw_step`` left zeroed."""
         for p in self.params:
             p._goat_fresh = True
 
@@ -117,7 +118,8 @@ class FlatParams(object):
 
     def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, grad_scale=1.0,
                    correct_bias=True):
-        """clip_grad_norm_(max_grad_norm) + AdamW (P/optim/adamw.py:85-110 numerics) on the flat buffer."""
+        """clip_grad_norm_(max_grad_norm) + AdamW (P/optim/adamw.py:85-110 numerics) on the flat buffer; the gradient
+        buffer is cleared in the same pass (weight-gradient GEMMs accumulate into it, see functional._wgrad)."""
         self.step_count += 1
         t = self.step_count
         # pageable source on purpose: the runtime stages a small pageable H2D copy before returning, so the
@@ -134,7 +136,7 @@ class FlatParams(object):
         _lib.check(L.goat_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                      self.shadow.data_ptr() if self.shadow is not None else None, sd, self.numel,
                                      self.n_decay, self._hp.data_ptr(), self._partial.data_ptr(), nparts.value,
-                                     self.grad_norm.data_ptr(), st), "goat_adamw_step")
+                                     self.grad_norm.data_ptr(), 1, st), "goat_adamw_step")
         ops.LAUNCHES[0] += 2
 
 
@@ -196,6 +198,8 @@ class TrainStep(object):
         else:
             self._fwd_bwd()
         self.launches_per_step = ops.LAUNCHES[0] - n0 + 2  # + sumsq + adamw
+        torch.cuda.synchronize()
+        flat.g.zero_()   # drop what the warm-up / capture passes accumulated
 
     def _fwd_bwd(self):
         self.flat.begin_step()

@@ -64,7 +64,7 @@ def _split_rows(t, params):
     return tuple(out)
 
 
-def _grad_into(params, fn, can_acc):
+def _grad_into(params, fn, can_acc, always_acc=False):
     """Produce the gradient of one parameter, or of several whose rows are concatenated (fused QKV).
 
     ``fn(out, acc)`` computes it into ``out`` (allocating when None), adding to the existing contents when
@@ -77,7 +77,9 @@ def _grad_into(params, fn, can_acc):
         fresh = [p._goat_fresh for p in params]
         if len(dsts) == 1 or runtime._adjacent(dsts):
             dst = dsts[0] if len(dsts) == 1 else runtime._fused_view(dsts)
-            if all(fresh):
+            if always_acc:
+                fn(dst, True)      # the flat gradient buffer is zero at step start (the optimizer kernel clears it)
+            elif all(fresh):
                 fn(dst, False)
             elif not any(fresh) and can_acc:
                 fn(dst, True)
@@ -99,8 +101,9 @@ def _grad_into(params, fn, can_acc):
 def _wgrad(params, dy_c, x_c):
     """dW = dY^T X for weight(s) [N,K] (rows of several weights concatenated)."""
     def fn(out, acc):
-        return ops.gemm(dy_c, x_c, a_mn=True, b_mn=True, out=out, res=out if acc else None, out_dtype=torch.float32)
-    return _grad_into(params, fn, True)
+        # split-K + atomic accumulate: into the (optimizer-zeroed) flat gradient view, or into fresh zeros
+        return ops.gemm(dy_c, x_c, a_mn=True, b_mn=True, out=out, accumulate=True)
+    return _grad_into(params, fn, True, always_acc=True)
 
 
 def _bgrad(params, dy_c):

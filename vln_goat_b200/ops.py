@@ -46,7 +46,8 @@ def _rowmajor2d(t, name):
 
 
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_out=None, out=None, out_dtype=None,
-         out2=None, act=ACT_NONE, alpha=1.0, drop_p=0.0, drop_seed=0, seed_ptr=None, force_simt=False):
+         out2=None, act=ACT_NONE, alpha=1.0, drop_p=0.0, drop_seed=0, seed_ptr=None, force_simt=False,
+         accumulate=False):
     """out[M,N] = epilogue(alpha * A B^T).  A: [M,K] (a_mn False) or [K,M] (a_mn True);
     B: [N,K] (b_mn False) or [K,N] (b_mn True).  See goat_gemm in include/goat_sm100.h."""
     _req_cuda(A, B, bias, res, aux_in, aux_out, out, out2)
@@ -57,7 +58,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
     if K != Kb or A.dtype != B.dtype:
         raise ValueError("gemm: A %s / B %s mismatch" % (tuple(A.shape), tuple(B.shape)))
     if out is None:
-        out = torch.empty((M, N), device=A.device, dtype=out_dtype or A.dtype)
+        if accumulate:
+            out = torch.zeros((M, N), device=A.device, dtype=torch.float32)
+        else:
+            out = torch.empty((M, N), device=A.device, dtype=out_dtype or A.dtype)
     a = _lib.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.dtype = dt(A)
@@ -87,6 +91,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
     a.act, a.alpha, a.drop_p, a.drop_seed = act, alpha, drop_p, drop_seed
     a.drop_seed_ptr = None if seed_ptr is None else seed_ptr.data_ptr()
     a.force_simt = int(force_simt)
+    a.accumulate = int(accumulate)
     _lib.check(_lib.lib().goat_gemm(C.byref(a), _stream()), "goat_gemm")
     LAUNCHES[0] += 1
     if GEMM_LOG is not None:
