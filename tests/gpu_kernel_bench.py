@@ -8,10 +8,11 @@ from vln_goat_b200 import ops
 dev = "cuda"
 dt = torch.bfloat16
 reps = int(os.environ.get("REPS", "20"))
+warm = int(os.environ.get("WARM", "3"))
 
 
 def timeit(name, fn, flops=None, bytes_=None):
-    for _ in range(3):
+    for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
