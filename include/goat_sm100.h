@@ -194,6 +194,63 @@ int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int sh
                     long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
                     int zero_grad, goat_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Attention pooling over the token axis of x [B,N,H] (fp32), softmax WITHOUT a mask (the reference pools over
+ * padding too, SURVEY.md 8a note 6).
+ *   mode 0  adaptive panorama fusion  P/model/vilmodel_goat.py:354-362, M/models/vilmodel_GOAT.py:727-733:
+ *           s_n = tanh(x_n . w + bias[0]);  a = softmax_n(s);  out = sum_n a_n x_n
+ *   mode 1  CFP pooling               P/model/pretrain_goat.py:502-515, M/models/vilmodel_GOAT.py:905-918:
+ *           s_n = tanh(x_n) . w;            a = softmax_n(s);  out = tanh(sum_n a_n x_n)
+ * fwd saves a [B,N] (and s [B,N] in mode 0).  bwd: dx [B,N,H] written; dw [H] and db [1] ACCUMULATED (caller zeroes).
+ * ------------------------------------------------------------------------------------------ */
+int goat_attn_pool_fwd(const float* x, const float* w, const float* bias, int mode, int B, int N, int H, float* out,
+                       float* a, float* s, goat_stream_t stream);
+int goat_attn_pool_bwd(const float* dout, const float* x, const float* w, const float* a, const float* s, const float* out,
+                       int mode, int B, int N, int H, float* dx, float* dw, float* db, goat_stream_t stream);
+
+/* p(z)-weighted dictionary sum of the back-door adjustment: out[b,:] = sum_n p[b,n] x[b,n,:]
+ * (M/models/vilmodel_GOAT.py:664-665 image z-dict, :107-111 instruction z-dicts).  p is data (no gradient). */
+int goat_wsum_fwd(const float* x, const float* p, int B, int N, int H, float* out, goat_stream_t stream);
+int goat_wsum_bwd(const float* dout, const float* p, int B, int N, int H, float* dx, goat_stream_t stream);
+
+/* "door" gate of BACL-text / FACL (M/models/vilmodel_GOAT.py:145-148, :548-552):
+ *   g = sigmoid(aug . wa + ba[0] + ori . wo + bo[0]);  out = g * aug + (1 - g) * ori      rows = tokens [M,H]
+ * bwd: daug / dori written; dwa, dwo [H], dba, dbo [1] ACCUMULATED (caller zeroes). */
+int goat_door_gate_fwd(const float* aug, const float* ori, const float* wa, const float* ba, const float* wo,
+                       const float* bo, int M, int H, float* out, float* gate, goat_stream_t stream);
+int goat_door_gate_bwd(const float* dout, const float* aug, const float* ori, const float* wa, const float* wo,
+                       const float* gate, int M, int H, float* daug, float* dori, float* dwa, float* dwo, float* dba,
+                       float* dbo, goat_stream_t stream);
+
+/* Row-wise softmax cross-entropy, F.cross_entropy(reduction='none') of the SAP / MLM / CFP losses
+ * (P/model/pretrain_goat.py:213-215, :348-350, :522-532; M/r2r/agent_base.py:133).  Element (i,j) of the logits is
+ * logits[i*stride_row + j*stride_col], so the transposed InfoNCE term needs no copy.  -inf logits are legal (masked
+ * actions).  labels int64; label == ignore_index gives loss 0 and no gradient.  lse [M] is saved for backward.
+ * bwd: dlogits(i,j) = dloss_i (softmax_ij - [j == label_i]), written or (accumulate=1) added at dlogits strides. */
+int goat_xent_fwd(const float* logits, long long stride_row, long long stride_col, const long long* labels, int M, int N,
+                  long long ignore_index, float* loss, float* lse, goat_stream_t stream);
+int goat_xent_bwd(const float* dloss, const float* logits, long long stride_row, long long stride_col,
+                  const long long* labels, const float* lse, int M, int N, long long ignore_index, float* dlogits,
+                  long long dstride_row, long long dstride_col, int accumulate, goat_stream_t stream);
+
+/* Gather-and-reduce over index lists: out[r,:] = scale * sum_{k<K, idx[r,k]>=0} src[idx[r,k],:], scale = 1 (sum) or
+ * 1/#valid (mean).  Replaces the host Python loops of global-map aggregation (P/model/vilmodel_goat.py:430-468: mean
+ * of the candidate-view embeddings that observed an unvisited node) and of the SAP / navigation logit fusion
+ * (P/model/pretrain_goat.py:328-345, M/models/vilmodel_GOAT.py:797-813) -- the index lists are built once on the
+ * host from the viewpoint-id strings.  idx int32 [R,K], -1 = empty slot.  bwd ACCUMULATES into dsrc (caller zeroes). */
+int goat_segment_reduce_fwd(const float* src, const int* idx, int R, int K, int H, int mean, float* out,
+                            goat_stream_t stream);
+int goat_segment_reduce_bwd(const float* dout, const int* idx, int R, int K, int H, int mean, float* dsrc,
+                            goat_stream_t stream);
+
+/* RoBERTa input embeddings before LayerNorm (P/model/Bert_backbone.py:87-116): out[m,:] = word[ids[m]] + pos[m % L] +
+ * type[0]  (position ids are arange(L) from 0, token types all 0).  bwd ACCUMULATES into the three tables (any may be
+ * NULL). */
+int goat_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type, int M, int L, int H,
+                   float* out, goat_stream_t stream);
+int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, float* dword, float* dpos, float* dtype,
+                   goat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -414,3 +414,168 @@ class LayerNormFn(torch.autograd.Function):
         dx32, _, dg, db, _ = _ln_bwd(dy.contiguous(), x32, gamma, mean, rstd, None, None, 0.0, 0, None, ctx.params[0],
                                      ctx.params[1])
         return dx32, dg, db, None, None
+
+
+# --------------------------------------------------------------------------------------
+# heads.cu composites: pooling, dictionary sums, door gate, cross-entropy, gather-reduce, embeddings
+# --------------------------------------------------------------------------------------
+def _acc_dst(param, shape=None):
+    """Destination a kernel can ACCUMULATE a parameter gradient into: the parameter's flat-gradient view when it
+    lives in an engine.FlatParams buffer (cleared first if nothing has written it this step), else fresh zeros that
+    are handed back to autograd.  -> (tensor, returned_to_autograd)"""
+    if param is None:
+        return None, False
+    d = getattr(param, "_goat_grad", None)
+    if d is not None and d.is_contiguous():
+        if param._goat_fresh:
+            d.zero_()
+            param._goat_fresh = False
+        return d, False
+    return torch.zeros(param.shape if shape is None else shape, device=param.device, dtype=torch.float32), True
+
+
+class AttnPoolFn(torch.autograd.Function):
+    """mode 0: out = sum_n softmax_n(tanh(x_n . w + b)) x_n  (adaptive panorama fusion, P/model/vilmodel_goat.py:354-362)
+    mode 1: out = tanh(sum_n softmax_n(tanh(x_n) . w) x_n)    (CFP pooling, P/model/pretrain_goat.py:502-515)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b, mode):
+        x = x.contiguous()
+        wv = w.detach().reshape(-1).contiguous()
+        out, a, s = ops.attn_pool_fwd(x, wv, None if b is None else b.detach().contiguous(), mode)
+        ctx.mode = mode
+        ctx.params = (w, b)
+        ctx.save_for_backward(x, wv, a, s, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wv, a, s, out = ctx.saved_tensors
+        w, b = ctx.params
+        dw, ret_w = _acc_dst(w)
+        db, ret_b = _acc_dst(b)
+        dx = ops.attn_pool_bwd(dout.contiguous(), x, wv, a, s, out, ctx.mode, dw.view(-1), None if db is None else db.view(-1))
+        return dx, (dw if ret_w else None), (db if ret_b else None), None
+
+
+class WSumFn(torch.autograd.Function):
+    """out[b] = sum_n p[b,n] x[b,n]   (BACL dictionary expectation, M/models/vilmodel_GOAT.py:664-665)"""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x = x.contiguous()
+        p = p.to(torch.float32).reshape(x.shape[0], x.shape[1]).contiguous()
+        ctx.save_for_backward(p)
+        ctx.N = x.shape[1]
+        return ops.wsum_fwd(x, p)
+
+    @staticmethod
+    def backward(ctx, dout):
+        p, = ctx.saved_tensors
+        return ops.wsum_bwd(dout.contiguous(), p, ctx.N), None
+
+
+class DoorGateFn(torch.autograd.Function):
+    """g = sigmoid(aug . wa + ba + ori . wo + bo); out = g aug + (1-g) ori   (M/models/vilmodel_GOAT.py:145-148, :548-552)"""
+
+    @staticmethod
+    def forward(ctx, aug, ori, wa, ba, wo, bo):
+        shp = aug.shape
+        a2 = aug.reshape(-1, shp[-1]).contiguous()
+        o2 = ori.reshape(-1, shp[-1]).contiguous()
+        wav, wov = wa.detach().reshape(-1).contiguous(), wo.detach().reshape(-1).contiguous()
+        out, gate = ops.door_gate_fwd(a2, o2, wav, ba.detach().contiguous(), wov, bo.detach().contiguous())
+        ctx.params = (wa, ba, wo, bo)
+        ctx.shp = shp
+        ctx.save_for_backward(a2, o2, wav, wov, gate)
+        return out.view(shp)
+
+    @staticmethod
+    def backward(ctx, dout):
+        a2, o2, wav, wov, gate = ctx.saved_tensors
+        wa, ba, wo, bo = ctx.params
+        dwa, r1 = _acc_dst(wa)
+        dba, r2 = _acc_dst(ba)
+        dwo, r3 = _acc_dst(wo)
+        dbo, r4 = _acc_dst(bo)
+        daug, dori = ops.door_gate_bwd(dout.reshape(a2.shape).contiguous(), a2, o2, wav, wov, gate, dwa.view(-1), dwo.view(-1),
+                                       dba.view(-1), dbo.view(-1))
+        return (daug.view(ctx.shp), dori.view(ctx.shp), dwa if r1 else None, dba if r2 else None, dwo if r3 else None,
+                dbo if r4 else None)
+
+
+class XentFn(torch.autograd.Function):
+    """F.cross_entropy(logits, labels, reduction='none') with ignore_index; logits may be a strided view (sim.T)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        if logits.dtype != torch.float32:
+            logits = logits.float()
+        labels = labels.contiguous()
+        loss, lse = ops.xent_fwd(logits, labels, ignore_index)
+        ctx.ignore_index = ignore_index
+        ctx.save_for_backward(logits, labels, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, lse = ctx.saved_tensors
+        return ops.xent_bwd(dloss.contiguous(), logits, labels, lse, ctx.ignore_index), None, None
+
+
+class SegmentReduceFn(torch.autograd.Function):
+    """out[r] = sum / mean over k of src[idx[r,k]] (idx -1 = empty)."""
+
+    @staticmethod
+    def forward(ctx, src, idx, mean):
+        src = src.contiguous()
+        ctx.mean, ctx.n_src = mean, src.shape[0]
+        ctx.save_for_backward(idx)
+        return ops.segment_reduce_fwd(src, idx, mean)
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx, = ctx.saved_tensors
+        return ops.segment_reduce_bwd(dout.contiguous(), idx, ctx.mean, ctx.n_src), None, None
+
+
+class EmbedFn(torch.autograd.Function):
+    """word[ids] + pos[arange(L)] + type[0]  -> [B*L, H]   (P/model/Bert_backbone.py:87-116, before LayerNorm)"""
+
+    @staticmethod
+    def forward(ctx, ids, word, pos, type_):
+        ids = ids.contiguous()
+        ctx.params = (word, pos, type_)
+        ctx.save_for_backward(ids)
+        return ops.embed_fwd(ids, word.detach(), pos.detach(), type_.detach())
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, = ctx.saved_tensors
+        word, pos, type_ = ctx.params
+        need = ctx.needs_input_grad
+        dw, rw = _acc_dst(word) if need[1] else (None, False)
+        dp, rp = _acc_dst(pos) if need[2] else (None, False)
+        dt_, rt = _acc_dst(type_) if need[3] else (None, False)
+        ops.embed_bwd(dout.contiguous(), ids, dw, dp, None if dt_ is None else dt_[0])
+        return None, (dw if rw else None), (dp if rp else None), (dt_ if rt else None)
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout on an fp32 tensor with the counter-based mask (regenerated in backward from the seed)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, seed_ptr):
+        x = x.contiguous()
+        ctx.p, ctx.seed, ctx.seed_ptr = p, seed, seed_ptr
+        return ops.cast(x, torch.float32, drop_p=p, drop_seed=seed, seed_ptr=seed_ptr)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.cast(dy.contiguous(), torch.float32, drop_p=ctx.p, drop_seed=ctx.seed, seed_ptr=ctx.seed_ptr), None, None, None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return DropoutFn.apply(x, float(p), next_seed(), seed_ptr())

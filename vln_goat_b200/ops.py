@@ -237,3 +237,181 @@ def cast(src, dtype, out=None, drop_p=0.0, drop_seed=0, seed_ptr=None):
                                             _p(seed_ptr), _stream()), "goat_dropout_cast")
     LAUNCHES[0] += 1
     return out
+
+
+# --------------------------------------------------------------------------------------
+# heads.cu: pooling, dictionary sums, door gate, cross-entropy, gather-reduce, embeddings (all fp32)
+# --------------------------------------------------------------------------------------
+def _f32c(t, name, shape=None):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("%s must be a contiguous fp32 tensor" % name)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t
+
+
+def attn_pool_fwd(x, w, bias, mode):
+    """x [B,N,H], w [H] (+ bias [1] in mode 0) -> (out [B,H], a [B,N], s [B,N] or None).  See goat_attn_pool_fwd."""
+    _req_cuda(x, w, bias)
+    B, N, H = x.shape
+    _f32c(x, "x"); _f32c(w, "w"); _f32c(bias, "bias")
+    if w.numel() != H:
+        raise ValueError("attn_pool: w must have H elements")
+    out = torch.empty((B, H), device=x.device, dtype=torch.float32)
+    a = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    s = torch.empty((B, N), device=x.device, dtype=torch.float32) if mode == 0 else None
+    _lib.check(_lib.lib().goat_attn_pool_fwd(_p(x), _p(w), _p(bias), mode, B, N, H, _p(out), _p(a), _p(s), _stream()),
+               "goat_attn_pool_fwd")
+    LAUNCHES[0] += 1
+    return out, a, s
+
+
+def attn_pool_bwd(dout, x, w, a, s, out, mode, dw, db):
+    """-> dx [B,N,H]; dw [H] / db [1] are accumulated into (pass zeroed or flat-gradient tensors)."""
+    _req_cuda(dout, x, w, a, dw, db)
+    B, N, H = x.shape
+    _f32c(dout, "dout", (B, H)); _f32c(dw, "dw"); _f32c(db, "db")
+    dx = torch.empty_like(x)
+    _lib.check(_lib.lib().goat_attn_pool_bwd(_p(dout), _p(x), _p(w), _p(a), _p(s), _p(out), mode, B, N, H, _p(dx), _p(dw),
+                                             _p(db), _stream()), "goat_attn_pool_bwd")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def wsum_fwd(x, p):
+    """x [B,N,H] fp32, p [B,N] fp32 -> out [B,H]"""
+    _req_cuda(x, p)
+    B, N, H = x.shape
+    _f32c(x, "x"); _f32c(p, "p", (B, N))
+    out = torch.empty((B, H), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_wsum_fwd(_p(x), _p(p), B, N, H, _p(out), _stream()), "goat_wsum_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def wsum_bwd(dout, p, N):
+    _req_cuda(dout, p)
+    B, H = dout.shape
+    _f32c(dout, "dout"); _f32c(p, "p", (B, N))
+    dx = torch.empty((B, N, H), device=dout.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_wsum_bwd(_p(dout), _p(p), B, N, H, _p(dx), _stream()), "goat_wsum_bwd")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def door_gate_fwd(aug, ori, wa, ba, wo, bo):
+    """aug, ori [M,H]; wa, wo [H]; ba, bo [1] -> (out [M,H], gate [M])"""
+    _req_cuda(aug, ori, wa, ba, wo, bo)
+    M, H = aug.shape
+    _f32c(aug, "aug"); _f32c(ori, "ori", (M, H)); _f32c(wa, "wa"); _f32c(wo, "wo"); _f32c(ba, "ba"); _f32c(bo, "bo")
+    out = torch.empty_like(aug)
+    gate = torch.empty((M,), device=aug.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_door_gate_fwd(_p(aug), _p(ori), _p(wa), _p(ba), _p(wo), _p(bo), M, H, _p(out), _p(gate),
+                                             _stream()), "goat_door_gate_fwd")
+    LAUNCHES[0] += 1
+    return out, gate
+
+
+def door_gate_bwd(dout, aug, ori, wa, wo, gate, dwa, dwo, dba, dbo):
+    """-> (daug, dori); dwa/dwo [H], dba/dbo [1] accumulated into."""
+    _req_cuda(dout, aug, ori, wa, wo, gate, dwa, dwo, dba, dbo)
+    M, H = aug.shape
+    _f32c(dout, "dout", (M, H))
+    for n, t in (("dwa", dwa), ("dwo", dwo), ("dba", dba), ("dbo", dbo)):
+        _f32c(t, n)
+    daug = torch.empty_like(aug)
+    dori = torch.empty_like(ori)
+    _lib.check(_lib.lib().goat_door_gate_bwd(_p(dout), _p(aug), _p(ori), _p(wa), _p(wo), _p(gate), M, H, _p(daug), _p(dori),
+                                             _p(dwa), _p(dwo), _p(dba), _p(dbo), _stream()), "goat_door_gate_bwd")
+    LAUNCHES[0] += 1
+    return daug, dori
+
+
+def xent_fwd(logits, labels, ignore_index=-100):
+    """logits fp32 [M,N] (any strides), labels int64 [M] -> (loss [M], lse [M])"""
+    _req_cuda(logits, labels)
+    if logits.dim() != 2 or logits.dtype != torch.float32:
+        raise ValueError("xent: logits must be 2-D fp32")
+    if labels.dtype != torch.int64 or labels.numel() != logits.shape[0] or not labels.is_contiguous():
+        raise ValueError("xent: labels must be contiguous int64 [M]")
+    M, N = logits.shape
+    loss = torch.empty((M,), device=logits.device, dtype=torch.float32)
+    lse = torch.empty((M,), device=logits.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_xent_fwd(_p(logits), logits.stride(0), logits.stride(1), _p(labels), M, N, ignore_index,
+                                        _p(loss), _p(lse), _stream()), "goat_xent_fwd")
+    LAUNCHES[0] += 1
+    return loss, lse
+
+
+def xent_bwd(dloss, logits, labels, lse, ignore_index=-100, out=None, accumulate=False):
+    """-> dlogits, shaped and strided like ``out`` (default: new contiguous [M,N])"""
+    _req_cuda(dloss, logits, labels, lse, out)
+    M, N = logits.shape
+    _f32c(dloss, "dloss", (M,))
+    if out is None:
+        out = torch.empty((M, N), device=logits.device, dtype=torch.float32)
+        accumulate = False
+    elif tuple(out.shape) != (M, N) or out.dtype != torch.float32:
+        raise ValueError("xent_bwd: bad out")
+    _lib.check(_lib.lib().goat_xent_bwd(_p(dloss), _p(logits), logits.stride(0), logits.stride(1), _p(labels), _p(lse), M, N,
+                                        ignore_index, _p(out), out.stride(0), out.stride(1), int(accumulate), _stream()),
+               "goat_xent_bwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def segment_reduce_fwd(src, idx, mean):
+    """src [R0,H] fp32, idx int32 [R,K] (-1 = empty) -> out [R,H]"""
+    _req_cuda(src, idx)
+    _f32c(src, "src")
+    if idx.dtype != torch.int32 or idx.dim() != 2 or not idx.is_contiguous():
+        raise ValueError("segment_reduce: idx must be contiguous int32 [R,K]")
+    R, K = idx.shape
+    H = src.shape[1]
+    out = torch.empty((R, H), device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_segment_reduce_fwd(_p(src), _p(idx), R, K, H, int(mean), _p(out), _stream()),
+               "goat_segment_reduce_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def segment_reduce_bwd(dout, idx, mean, n_src):
+    _req_cuda(dout, idx)
+    R, K = idx.shape
+    H = dout.shape[1]
+    _f32c(dout, "dout", (R, H))
+    dsrc = torch.zeros((n_src, H), device=dout.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_segment_reduce_bwd(_p(dout), _p(idx), R, K, H, int(mean), _p(dsrc), _stream()),
+               "goat_segment_reduce_bwd")
+    LAUNCHES[0] += 2
+    return dsrc
+
+
+def embed_fwd(ids, word, pos, type_):
+    """ids int64 [B,L] -> [B*L,H] fp32 = word[ids] + pos[arange(L)] + type[0]"""
+    _req_cuda(ids, word, pos, type_)
+    if ids.dtype != torch.int64 or ids.dim() != 2 or not ids.is_contiguous():
+        raise ValueError("embed: ids must be contiguous int64 [B,L]")
+    B, L = ids.shape
+    H = word.shape[1]
+    _f32c(word, "word"); _f32c(pos, "pos"); _f32c(type_, "type")
+    if L > pos.shape[0]:
+        raise ValueError("embed: sequence length %d exceeds the %d learned positions" % (L, pos.shape[0]))
+    out = torch.empty((B * L, H), device=ids.device, dtype=torch.float32)
+    _lib.check(_lib.lib().goat_embed_fwd(_p(ids), _p(word), _p(pos), _p(type_), B * L, L, H, _p(out), _stream()),
+               "goat_embed_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def embed_bwd(dout, ids, dword, dpos, dtype_):
+    """accumulates into the given gradient tables (any may be None)"""
+    _req_cuda(dout, ids, dword, dpos, dtype_)
+    B, L = ids.shape
+    H = dout.shape[1]
+    _f32c(dout, "dout", (B * L, H)); _f32c(dword, "dword"); _f32c(dpos, "dpos"); _f32c(dtype_, "dtype")
+    _lib.check(_lib.lib().goat_embed_bwd(_p(dout), _p(ids), B * L, L, H, _p(dword), _p(dpos), _p(dtype_), _stream()),
+               "goat_embed_bwd")
+    LAUNCHES[0] += 1
