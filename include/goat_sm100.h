@@ -245,11 +245,12 @@ int goat_segment_reduce_bwd(const float* dout, const int* idx, int R, int K, int
 
 /* RoBERTa input embeddings before LayerNorm (P/model/Bert_backbone.py:87-116): out[m,:] = word[ids[m]] + pos[m % L] +
  * type[0]  (position ids are arange(L) from 0, token types all 0).  bwd ACCUMULATES into the three tables (any may be
- * NULL). */
+ * NULL); rows equal to padding_idx (< 0: none) of the word and position tables receive no gradient, as with
+ * nn.Embedding(padding_idx=...) (the fine-tune config inherits roberta's pad_token_id = 1). */
 int goat_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type, int M, int L, int H,
                    float* out, goat_stream_t stream);
-int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, float* dword, float* dpos, float* dtype,
-                   goat_stream_t stream);
+int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, long long padding_idx, float* dword,
+                   float* dpos, float* dtype, goat_stream_t stream);
 
 #ifdef __cplusplus
 }

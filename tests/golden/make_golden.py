@@ -201,14 +201,93 @@ def gen_nav():
     save("bacl_image", view=view, zf=zf, pz=pz, out=y)
 
 
+def _keys_blob(module):
+    return np.array("\n".join(module.state_dict().keys()))
+
+
+def gen_pretrain_full():
+    """Full pretrain model (208 M parameters, seeded): MLM / SAP / CFP on one synthetic batch (tests/synth.py)."""
+    ref_shim.install("pretrain")
+    from model.pretrain_goat import GlocalTextPathCMTPreTraining
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    cfg = ref_shim.pretrain_config()
+    model = load_seeded(GlocalTextPathCMTPreTraining(cfg).eval(), seed=20)
+    model.tie_weights()
+    batch = synth.pretrain_batch(B=3, L=24, seed=5)
+    out = {"state_dict_keys": _keys_blob(model)}
+    # MLM
+    model.zero_grad()
+    scores = model(batch, "mlm", compute_loss=False)
+    loss = model(batch, "mlm", compute_loss=True)
+    loss.sum().backward()
+    out.update(mlm_scores_digest=digest(scores), mlm_scores_head=scores[:, :64], mlm_loss=loss)
+    out.update({"mlm." + k: v for k, v in grads_digest(model).items()})
+    # SAP
+    model.zero_grad()
+    gl, ll, fl, _, _ = model(batch, "sap", compute_loss=False)
+    loss = model(batch, "sap", compute_loss=True)
+    loss.sum().backward()
+    out.update(sap_global_logits=gl, sap_local_logits=ll, sap_fused_logits=fl, sap_loss=loss)
+    out.update({"sap." + k: v for k, v in grads_digest(model).items()})
+    # CFP (the reference hard-codes .cuda() on the target, P/model/pretrain_goat.py:520)
+    model.zero_grad()
+    go, vo, fo, to = model(batch, "cfp", compute_loss=False)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        loss = model(batch, "cfp", compute_loss=True)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    loss.sum().backward()
+    out.update(cfp_gmap=go, cfp_vp=vo, cfp_fused=fo, cfp_txt=to, cfp_loss=loss)
+    out.update({"cfp." + k: v for k, v in grads_digest(model).items()})
+    save("pretrain_full", **out)
+
+
+def gen_nav_full():
+    """Full fine-tune model with BACL + FACL on: language -> panorama -> navigation on synthetic step inputs."""
+    ref_shim.install("nav")
+    import models.vilmodel_GOAT as V
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    from collections import defaultdict
+    cfg = ref_shim.nav_config()
+    model = load_seeded(V.GlocalTextPathNavCMT(cfg).eval(), seed=21)
+    lang, pano, nav = synth.nav_inputs(B=3, L=20, seed=6)
+    dd = lambda d: defaultdict(lambda: None, d)
+    txt = model("language", dd(lang))
+    pe, pm, pf = model("panorama", dd(pano))
+    navb = dict(nav)
+    mem = navb.pop("mem_embeds")
+    navb["txt_embeds"] = txt
+    navb["vp_img_embeds"] = torch.cat([torch.zeros_like(pe[:, :1]), mem.unsqueeze(1), pe], 1)
+    outs = model("navigation", dd(navb))
+    g = torch.Generator().manual_seed(99)
+    w_cls = torch.randn(outs["cls_embeds"].shape, generator=g)
+    w_pf = torch.randn(pf.shape, generator=g)
+    target = torch.tensor([4, 0, 5])      # an unvisited node / [stop] / an unvisited node
+    loss = torch.nn.functional.cross_entropy(outs["fused_logits"], target, reduction="sum") + \
+        (outs["cls_embeds"] * w_cls).sum() + (pf * w_pf).sum()
+    loss.backward()
+    save("nav_full", state_dict_keys=_keys_blob(model), txt_embeds=txt, pano_embeds=pe, pano_masks=pm, pano_fused=pf,
+         global_logits=outs["global_logits"], local_logits=outs["local_logits"], fused_logits=outs["fused_logits"],
+         cls_embeds=outs["cls_embeds"], gmap_embeds=outs["gmap_embeds"], vp_embeds=outs["vp_embeds"], w_cls=w_cls,
+         w_pf=w_pf, target=target, loss=loss.detach(), **grads_digest(model))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tree", choices=["pretrain", "nav", "all"], default="all")
+    ap.add_argument("--tree", choices=["pretrain", "nav", "pretrain_full", "nav_full", "all"], default="all")
     a = ap.parse_args()
     if a.tree == "all":
-        for t in ("pretrain", "nav"):
+        for t in ("pretrain", "nav", "pretrain_full", "nav_full"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "--tree", t])
     elif a.tree == "pretrain":
         gen_pretrain()
+    elif a.tree == "pretrain_full":
+        gen_pretrain_full()
+    elif a.tree == "nav_full":
+        gen_nav_full()
     else:
         gen_nav()

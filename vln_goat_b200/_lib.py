@@ -94,8 +94,8 @@ SYMBOLS = {
                                           C.c_void_p]),
     "goat_embed_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p]),
-    "goat_embed_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p]),
+    "goat_embed_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

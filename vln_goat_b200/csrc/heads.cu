@@ -332,13 +332,15 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
   out[(size_t)m * H + h] = word[(size_t)id * H + h] + pos[(size_t)(m % L) * H + h] + type[h];
 }
 __global__ void embed_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ ids, int L, int H,
-                                 float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype) {
+                                 long long pad, float* __restrict__ dword, float* __restrict__ dpos,
+                                 float* __restrict__ dtype) {
   const int m = blockIdx.y;
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const float g = dout[(size_t)m * H + h];
-  if (dword) atomicAdd(dword + (size_t)ids[m] * H + h, g);
-  if (dpos) atomicAdd(dpos + (size_t)(m % L) * H + h, g);
+  // nn.Embedding(padding_idx=pad) never accumulates a gradient into row `pad` (word AND position tables)
+  if (dword && ids[m] != pad) atomicAdd(dword + (size_t)ids[m] * H + h, g);
+  if (dpos && (long long)(m % L) != pad) atomicAdd(dpos + (size_t)(m % L) * H + h, g);
   if (dtype) atomicAdd(dtype + h, g);
 }
 
@@ -479,13 +481,13 @@ int goat_embed_fwd(const long long* ids, const float* word, const float* pos, co
   return GOAT_OK;
 }
 
-int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, float* dword, float* dpos, float* dtype,
-                   goat_stream_t stream) {
+int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, long long padding_idx, float* dword,
+                   float* dpos, float* dtype, goat_stream_t stream) {
   GOAT_CHECK(dout && ids, "goat_embed_bwd: null argument");
   if (M <= 0 || H <= 0) return GOAT_OK;
   GOAT_CHECK(M <= 65535, "goat_embed_bwd: too many tokens per call (max 65535)");
-  embed_bwd_kernel<<<dim3((H + 127) / 128, M), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, ids, L, H, dword,
-                                                                                                dpos, dtype);
+  embed_bwd_kernel<<<dim3((H + 127) / 128, M), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, ids, L, H,
+                                                                                                padding_idx, dword, dpos, dtype);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

@@ -543,9 +543,10 @@ class EmbedFn(torch.autograd.Function):
     """word[ids] + pos[arange(L)] + type[0]  -> [B*L, H]   (P/model/Bert_backbone.py:87-116, before LayerNorm)"""
 
     @staticmethod
-    def forward(ctx, ids, word, pos, type_):
+    def forward(ctx, ids, word, pos, type_, padding_idx=-1):
         ids = ids.contiguous()
         ctx.params = (word, pos, type_)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
         ctx.save_for_backward(ids)
         return ops.embed_fwd(ids, word.detach(), pos.detach(), type_.detach())
 
@@ -557,8 +558,8 @@ class EmbedFn(torch.autograd.Function):
         dw, rw = _acc_dst(word) if need[1] else (None, False)
         dp, rp = _acc_dst(pos) if need[2] else (None, False)
         dt_, rt = _acc_dst(type_) if need[3] else (None, False)
-        ops.embed_bwd(dout.contiguous(), ids, dw, dp, None if dt_ is None else dt_[0])
-        return None, (dw if rw else None), (dp if rp else None), (dt_ if rt else None)
+        ops.embed_bwd(dout.contiguous(), ids, dw, dp, None if dt_ is None else dt_[0], ctx.padding_idx)
+        return None, (dw if rw else None), (dp if rp else None), (dt_ if rt else None), None
 
 
 class DropoutFn(torch.autograd.Function):

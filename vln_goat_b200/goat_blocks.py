@@ -44,6 +44,8 @@ class RobertaEmbeddings(nn.Module):
         self.config = config
         self.tuple_output = tuple_output
         self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
+        # registered here so the state_dict order is the reference's (word, position, type); re-created below
+        self.position_embeddings = nn.Embedding(1, 1)
         self.token_type_embeddings = nn.Embedding(config.type_vocab_size, config.hidden_size)
         self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
@@ -57,7 +59,7 @@ class RobertaEmbeddings(nn.Module):
             raise RuntimeError("vln_goat_b200 blocks need CUDA tensors: there is no CPU fallback on this path")
         B, L = input_ids.shape
         s = Fn.EmbedFn.apply(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
-                             self.token_type_embeddings.weight)
+                             self.token_type_embeddings.weight, self.padding_idx)
         y32, _ = Fn.LayerNormFn.apply(s, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, torch.float32)
         y32 = Fn.dropout(y32, self.dropout.p, self.training)
         return y32.view(B, L, -1)

@@ -406,12 +406,12 @@ def embed_fwd(ids, word, pos, type_):
     return out
 
 
-def embed_bwd(dout, ids, dword, dpos, dtype_):
-    """accumulates into the given gradient tables (any may be None)"""
+def embed_bwd(dout, ids, dword, dpos, dtype_, padding_idx=-1):
+    """accumulates into the given gradient tables (any may be None); row ``padding_idx`` of word / pos gets nothing"""
     _req_cuda(dout, ids, dword, dpos, dtype_)
     B, L = ids.shape
     H = dout.shape[1]
     _f32c(dout, "dout", (B * L, H)); _f32c(dword, "dword"); _f32c(dpos, "dpos"); _f32c(dtype_, "dtype")
-    _lib.check(_lib.lib().goat_embed_bwd(_p(dout), _p(ids), B * L, L, H, _p(dword), _p(dpos), _p(dtype_), _stream()),
-               "goat_embed_bwd")
+    _lib.check(_lib.lib().goat_embed_bwd(_p(dout), _p(ids), B * L, L, H, int(padding_idx), _p(dword), _p(dpos), _p(dtype_),
+                                         _stream()), "goat_embed_bwd")
     LAUNCHES[0] += 1
