@@ -129,6 +129,7 @@ def test_xent_rows_inf_ignore_and_transposed(M, N):
     assert maxerr(out, ref) < 2e-5
     assert maxerr(xc.grad, xr.grad) < 2e-6
     if M == N:                            # transposed view, as the symmetric InfoNCE uses it
+        x = torch.randn(M, N, generator=g) * 3      # no masked column: its transpose would be an all -inf row
         xr2 = x.clone().requires_grad_(True)
         tgt = torch.arange(M)
         ref2 = F.cross_entropy(xr2.t(), tgt, reduction="none")
