@@ -11,15 +11,31 @@ reps = int(os.environ.get("REPS", "20"))
 warm = int(os.environ.get("WARM", "3"))
 
 
+use_graph = os.environ.get("GRAPH", "1") == "1" and warm > 0
+
+
 def timeit(name, fn, flops=None, bytes_=None):
+    """Device time per call.  The launches are captured in a CUDA graph (reps calls per replay) so that the
+    Python / ctypes / tensor-map-encode host cost of each call (tens of microseconds) does not hide the kernel time."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
+    if use_graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     extra = ""

@@ -19,6 +19,7 @@
 // exp, row sums in registers), writes P (and dS) as 16-bit operands back to shared memory for the second MMA.
 // TMEM budget: 256 columns (S 128 + O 64 forward; S 128 + dP 128, then reused for dV 64 | dK 64 | dQ 64 backward).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ float drop_mul(const TcArgs& p, unsigned long long se
 struct Smem {
   uint8_t* base;
   __device__ explicit Smem(uint8_t* raw) {
-    base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    base = smem_align1024(raw);
   }
 };
 
@@ -576,10 +577,26 @@ bool attn_tc_eligible(const goat_attn_args* a, bool bwd) {
   return true;
 }
 
+bool attn_pipe_eligible(const goat_attn_args* a);
+int attn_fwd_pipe(const goat_attn_args* a, cudaStream_t st);
+int attn_bwd_pipe(const goat_attn_args* a, cudaStream_t st);
+
+// GOAT_ATTN_LEGACY=1 keeps the one-CTA-per-(head,batch) kernels of this file for every shape (A/B comparisons)
+static bool legacy_only() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GOAT_ATTN_LEGACY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int attn_fwd_tc(const goat_attn_args* a, cudaStream_t st) {
+  if (!legacy_only() && attn_pipe_eligible(a)) return attn_fwd_pipe(a, st);
   return a->dtype == GOAT_F16 ? fwd_launch<__half>(a, st) : fwd_launch<__nv_bfloat16>(a, st);
 }
 int attn_bwd_tc(const goat_attn_args* a, cudaStream_t st) {
+  if (!legacy_only() && attn_pipe_eligible(a)) return attn_bwd_pipe(a, st);
   return a->dtype == GOAT_F16 ? bwd_launch<__half>(a, st) : bwd_launch<__nv_bfloat16>(a, st);
 }
 

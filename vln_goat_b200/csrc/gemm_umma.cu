@@ -143,7 +143,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(BLOCK_N == 128, "tile scheduler and TMEM double buffering assume 128-wide tiles");
   using C = Cfg<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   float* patches = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
