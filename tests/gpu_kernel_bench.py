@@ -14,7 +14,12 @@ warm = int(os.environ.get("WARM", "3"))
 use_graph = os.environ.get("GRAPH", "1") == "1" and warm > 0
 
 
+only = [x for x in os.environ.get("ONLY", "").split(",") if x]
+
+
 def timeit(name, fn, flops=None, bytes_=None):
+    if only and not any(x in name for x in only):
+        return
     """Device time per call.  The launches are captured in a CUDA graph (reps calls per replay) so that the
     Python / ctypes / tensor-map-encode host cost of each call (tens of microseconds) does not hide the kernel time."""
     for _ in range(warm):

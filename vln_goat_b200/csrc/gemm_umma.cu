@@ -16,6 +16,7 @@
 // major-ness goes into the instruction descriptor and the smem matrix descriptors.
 // Ragged M / N / K edges: TMA zero-fills out-of-bounds box elements; the epilogue predicates stores.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -303,6 +304,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
 }
 
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -339,8 +342,6 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint
   return GOAT_OK;
 }
 
-}  // namespace
-
 // 3-D map over a token-major [d2 = batch][d1 = token][d0 = channel] tensor (channel contiguous, token stride ld,
 // batch stride sb, in elements); boxes of box0 channels x box1 tokens x 1 batch, 128B swizzle, zero OOB fill.
 int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
@@ -360,8 +361,6 @@ int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64
   return GOAT_OK;
 }
 
-namespace {
-
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -371,6 +370,10 @@ int num_sms() {
   }
   return n;
 }
+
+int gemm_umma2(const goat_gemm_args& a, const EpiParams& ep, int block_n, cudaStream_t stream);
+
+namespace {
 
 template <typename T, int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
@@ -428,7 +431,25 @@ bool gemm_umma_eligible(const goat_gemm_args& a) {
   return true;
 }
 
+// Tile selection.  M <= 128 (heads, poolers): one CTA per 128 x 128 tile.  Otherwise a CTA pair per 256 x BLOCK_N tile
+// (gemm_umma2.cu); 256-wide tiles halve the L2 bytes per FLOP and are taken when enough of them exist to occupy most
+// of the 74 pairs.  GOAT_GEMM_2CTA=0 / GOAT_GEMM_BN=128|256 override (tuning and A/B measurements).
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 int gemm_umma(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
+  static const int use2 = env_int("GOAT_GEMM_2CTA", 1);
+  static const int force_bn = env_int("GOAT_GEMM_BN", 0);
+  if (use2 && a.M > 128) {
+    int bn = force_bn;
+    if (bn != 128 && bn != 256) {
+      const int tiles256 = ((a.M + 255) / 256) * ((a.N + 255) / 256);
+      bn = (a.N >= 256 && (ep.accumulate || tiles256 >= 48)) ? 256 : 128;
+    }
+    return gemm_umma2(a, ep, bn, stream);
+  }
   if (a.dtype == GOAT_F16) return dispatch<__half>(a, ep, stream);
   return dispatch<__nv_bfloat16>(a, ep, stream);
 }
