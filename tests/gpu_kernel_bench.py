@@ -81,6 +81,25 @@ if which in ("all", "gemm"):
     timeit("wgrad qkv 2304x768x5120 acc", lambda: ops.gemm(dqkv, x, a_mn=True, b_mn=True, out=g2304, accumulate=True), 2 * M * 2304 * 768)
     timeit("wgrad ffn1 3072x768x5120 acc", lambda: ops.gemm(dz, x, a_mn=True, b_mn=True, out=g3072, accumulate=True), 2 * M * 3072 * 768)
     timeit("wgrad ffn2 768x3072x5120 acc", lambda: ops.gemm(dy, h, a_mn=True, b_mn=True, out=g768x, accumulate=True), 2 * M * 3072 * 768)
+if which in ("all", "gemm", "gemmvp"):
+    Mv = 2368
+    xv = torch.randn(Mv, 768, device=dev).to(dt); xv32 = torch.randn(Mv, 768, device=dev)
+    hv = torch.randn(Mv, 3072, device=dev).to(dt); zv = torch.empty(Mv, 3072, device=dev, dtype=dt)
+    dqkvv = torch.randn(Mv, 2304, device=dev).to(dt); dzv = torch.randn(Mv, 3072, device=dev).to(dt)
+    Wkv = (torch.randn(1536, 768, device=dev) * 0.02).to(dt); b15 = torch.zeros(1536, device=dev)
+    dkv = torch.randn(M, 1536, device=dev).to(dt); g1536 = torch.zeros(1536, 768, device=dev)
+    timeit("fwd kv    5120x1536x768 +bias", lambda: ops.gemm(x, Wkv, bias=b15), 2 * M * 1536 * 768)
+    timeit("dgrad kv  5120x768x1536 f32out", lambda: ops.gemm(dkv, Wkv, b_mn=True, out_dtype=torch.float32), 2 * M * 1536 * 768)
+    timeit("wgrad kv  1536x768x5120 acc", lambda: ops.gemm(dkv, x, a_mn=True, b_mn=True, out=g1536, accumulate=True), 2 * M * 1536 * 768)
+    timeit("vp fwd qkv 2368x2304x768 +bias", lambda: ops.gemm(xv, Wqkv, bias=b3), 2 * Mv * 2304 * 768)
+    timeit("vp fwd out 2368x768x768 +bias+res+drop f32", lambda: ops.gemm(xv, Wo, bias=b0, res=xv32, out_dtype=torch.float32, drop_p=0.1, drop_seed=5), 2 * Mv * 768 * 768)
+    timeit("vp fwd ffn1 2368x3072x768 gelu", lambda: ops.gemm(xv, W1, bias=b1, act=ops.ACT_GELU, aux_out=zv), 2 * Mv * 3072 * 768)
+    timeit("vp fwd ffn2 2368x768x3072 +res+drop f32", lambda: ops.gemm(hv, W2, bias=b0, res=xv32, out_dtype=torch.float32, drop_p=0.1, drop_seed=5), 2 * Mv * 768 * 3072)
+    timeit("vp dgrad ffn2 2368x3072x768 dgelu", lambda: ops.gemm(xv, W2, b_mn=True, act=ops.ACT_DGELU, aux_in=zv), 2 * Mv * 3072 * 768)
+    timeit("vp dgrad ffn1 2368x768x3072 +res f32", lambda: ops.gemm(dzv, W1, b_mn=True, res=xv32, out_dtype=torch.float32), 2 * Mv * 768 * 3072)
+    timeit("vp dgrad out 2368x768x768", lambda: ops.gemm(xv, Wo, b_mn=True), 2 * Mv * 768 * 768)
+    timeit("vp wgrad out 768x768x2368 acc", lambda: ops.gemm(xv, xv, a_mn=True, b_mn=True, out=g768, accumulate=True), 2 * Mv * 768 * 768)
+    timeit("vp wgrad ffn1 3072x768x2368 acc", lambda: ops.gemm(dzv, xv, a_mn=True, b_mn=True, out=g3072, accumulate=True), 2 * Mv * 3072 * 768)
 if which in ("all", "attn"):
     B, L, Nq = 64, 80, 37
     qkv = torch.randn(B, L, 2304, device=dev).to(dt)

@@ -123,13 +123,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// cdf = Phi(x), e = exp(-x^2 / 2).  h = erfc(|x| / sqrt 2) / 2 = Phi(-|x|) from the A&S polynomial (coefficients pre-halved),
+// then Phi(x) = x >= 0 ? 1 - h : h.  ~15 instructions per element including the two MUFU ops.
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-  const float u = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  e = ex2_approx(-u * u * 1.4426950408889634f);          // exp(-x^2 / 2)
-  const float erf_abs = 1.0f - poly * e;
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  e = ex2_approx(x * x * -0.72134752044448170368f);      // exp(-x^2 / 2)
+  const float h = p * t * e;
+  cdf = x >= 0.0f ? 1.0f - h : h;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float cdf, e;

@@ -446,7 +446,7 @@ int gemm_umma(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream)
     int bn = force_bn;
     if (bn != 128 && bn != 256) {
       const int tiles256 = ((a.M + 255) / 256) * ((a.N + 255) / 256);
-      bn = (a.N >= 256 && (ep.accumulate || tiles256 >= 48)) ? 256 : 128;
+      bn = (a.N >= 256 && (ep.accumulate || tiles256 >= 40)) ? 256 : 128;
     }
     return gemm_umma2(a, ep, bn, stream);
   }

@@ -29,6 +29,13 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint
               uint32_t box_inner, uint32_t box_outer);
 int num_sms();
 
+#ifdef GOAT_TIMELINE
+__device__ long long g_timeline[4096];
+#define TL(slot, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_timeline[(slot) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define TL(slot, idx) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;   // rows of A per CTA; the pair tile is 256 rows
@@ -83,7 +90,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into this CTA's smem whose transaction bytes complete on a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -207,9 +214,10 @@ __device__ __forceinline__ void epi_out4(const EpiParams& ep, int m, int n, floa
   }
 }
 
-// predicated scalar path for ragged patches and the GENERIC mode (kept out of line: it is cold)
+// predicated scalar path for ragged patches and the GENERIC mode (kept out of line: it is cold).  `ep` BY VALUE: taking
+// the address of the kernel parameter would give it a stack copy that the hot loops then re-read (LDL) after every store.
 template <typename T>
-__device__ __noinline__ void epi_patch_scalar(const EpiParams& ep, const float* patch, int mrow0, int nc, int M, int N, int rl,
+__device__ __noinline__ void epi_patch_scalar(const EpiParams ep, const float* patch, int mrow0, int nc, int M, int N, int rl,
                                               int c4) {
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {
@@ -268,8 +276,10 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
     int nm0 = 0, nn0 = 0, nkb0 = 0, nkb1 = 0;
     const bool has_next = t + cx.num_clusters < sc.num_tiles;
     if (has_next) tile_coords2<BN>(sc, t + cx.num_clusters, nm0, nn0, nkb0, nkb1);
+    if (cx.lane == 0 && cx.lg == 0 && cx.col_off == 0) TL(4, local);
     mbar_wait(&cx.tmem_full_bar[buf], ((uint32_t)local >> 1) & 1);
     tcgen05_fence_after();
+    if (cx.lane == 0 && cx.lg == 0 && cx.col_off == 0) TL(5, local);
     const uint32_t tacc = cx.tmem_base + (uint32_t)(buf * BN + cx.col_off) + ((uint32_t)(cx.lg * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
@@ -287,6 +297,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
         if (nxt_full) prefetch_patch<T, MODE>(ep, nm0 + cx.row_off, nn0 + cx.col_off + c4, rl, nxt);
       }
       tmem_ld_wait();
+      if (cx.lane == 0 && cx.lg == 0 && cx.col_off == 0) TL(8, local * NCH + c);
       if (c == NCH - 1) {
         // every TMEM read of this warp for this tile is done: hand the accumulator back to the leader's MMA warp
         tcgen05_fence_before();
@@ -298,24 +309,29 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
           *reinterpret_cast<float4*>(patch + cx.lane * PATCH_LD + j) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         __syncwarp();
+        if (cx.lane == 0 && cx.lg == 0 && cx.col_off == 0) TL(9, local * NCH + c);
         if (cur_full) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (MODE != EPI_ACC && ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + c4));
+          // all 8 smem reads first: a generic-pointer global store may alias shared memory as far as the compiler
+          // knows, so interleaved LDS / ST would be issued strictly in program order (one row at a time)
+          float4 acc[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row_l = i * 4 + rl;
-            const float4 acc = *reinterpret_cast<const float4*>(patch + row_l * PATCH_LD + c4);
-            epi_out4<T, MODE>(ep, mrow0 + row_l, nc + c4, acc, b4, cur, i, keep, seed);
-          }
+          for (int i = 0; i < 8; ++i) acc[i] = *reinterpret_cast<const float4*>(patch + (i * 4 + rl) * PATCH_LD + c4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            epi_out4<T, MODE>(ep, mrow0 + i * 4 + rl, nc + c4, acc[i], b4, cur, i, keep, seed);
         } else {
           epi_patch_scalar<T>(ep, patch, mrow0, nc, M, N, rl, c4);
         }
         __syncwarp();
+        if (cx.lane == 0 && cx.lg == 0 && cx.col_off == 0) TL(10, local * NCH + c);
       }
       cur = nxt;
       cur_full = nxt_full;
     }
     m0 = nm0; n0 = nn0; kb0 = nkb0; kb1 = nkb1;
+    if (cx.lane == 0 && cx.lg == 0 && cx.col_off == 0) TL(6, local);
   }
 }
 
@@ -337,6 +353,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TL(7, 2);
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
@@ -361,6 +378,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(7, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -405,14 +423,17 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int m0, n0, kb0, kb1;
         tile_coords2<BN>(sc, t, m0, n0, kb0, kb1);
         const int buf = local & 1;
+        TL(0, local);
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)local >> 1) & 1) ^ 1);   // both epilogues drained this accumulator
         tcgen05_fence_after();
+        TL(1, local);
         const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
+          if (kb == kb0) TL(2, local);
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
@@ -426,6 +447,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           umma_commit_2sm(&empty_bar[s]);  // frees this smem stage in both CTAs
         }
         umma_commit_2sm(&tmem_full_bar[buf]);  // accumulator complete, both CTAs' epilogues may read
+        TL(3, local);
       }
     }
   } else {
@@ -454,6 +476,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  if (threadIdx.x == 0) TL(7, 1);
   tcgen05_fence_before();
   cluster_sync_all();   // the peer's smem / barriers / TMEM stay valid until both CTAs are done
   if (warp == 1) tmem_dealloc_2sm<2 * BN>(tmem_base);
@@ -521,6 +544,12 @@ int dispatch2(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream)
 }
 
 }  // namespace
+
+#ifdef GOAT_TIMELINE
+extern "C" int goat_debug_timeline(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 4096);
+}
+#endif
 
 // block_n: 128 or 256
 int gemm_umma2(const goat_gemm_args& a, const EpiParams& ep, int block_n, cudaStream_t stream) {
