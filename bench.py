@@ -355,22 +355,46 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
     dev = torch.device("cuda", torch.cuda.current_device())
     tot_ms, tot_flop = 0.0, 0.0
     umma_ms, umma_flop, n_umma = 0.0, 0.0, 0
-    for (M, N, K, a_mn, b_mn, dt_, simt), cnt in uniq.items():
+    for (M, N, K, a_mn, b_mn, dt_, simt, acc_, act, has_bias, has_res, out32, has_drop, has_out2), cnt in uniq.items():
         dt_t = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}[dt_]
         A = torch.randn((K, M) if a_mn else (M, K), device=dev).to(dt_t)
         Bm = torch.randn((K, N) if b_mn else (N, K), device=dev).to(dt_t)
-        out = torch.empty((M, N), device=dev, dtype=dt_t)
+        out = (torch.zeros if acc_ else torch.empty)((M, N), device=dev, dtype=torch.float32 if out32 else dt_t)
+        kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), out=out, accumulate=bool(acc_), act=act)
+        if has_bias:
+            kw["bias"] = torch.zeros(N, device=dev)
+        if has_res:
+            kw["res"] = torch.randn(M, N, device=dev)
+        if has_drop:
+            kw["drop_p"], kw["drop_seed"] = 0.1, 11
+        if has_out2:
+            kw["out2"] = torch.empty((M, N), device=dev, dtype=dt_t)
+        if act == ops.ACT_GELU:
+            kw["aux_out"] = torch.empty((M, N), device=dev, dtype=dt_t)
+        if act in (ops.ACT_DGELU, ops.ACT_DRELU):
+            kw["aux_in"] = torch.randn(M, N, device=dev).to(dt_t)
+
+        def launch():
+            ops.gemm(A, Bm, **kw)
         for _ in range(3):
-            ops.gemm(A, Bm, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out)
-        reps = 10
+            launch()
+        reps = 20
+        # `reps` launches captured in one CUDA graph: the event pair sees device time, not the ~20 us of Python /
+        # ctypes / tensor-map encoding per call (the step itself is replayed as a graph, too)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                launch()
+        g.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
-            ops.gemm(A, Bm, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out)
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        del g
         fl = 2.0 * M * N * K
         tot_ms += ms * cnt
         tot_flop += fl * cnt
@@ -379,7 +403,8 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
             umma_flop += fl * cnt
             n_umma += cnt
     achieved = umma_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
-    return {"bound": "tensor", "kernel": "gemm_umma_kernel (tcgen05.mma + TMA, all %d launches of one step)" % n_umma,
+    return {"bound": "tensor", "kernel": "gemm_umma2_kernel / gemm_umma_kernel (tcgen05.mma cta_group::2 + TMA; all %d tensor-core GEMM launches of one step, "
+                      "each shape re-timed as 20 graph-captured launches)" % n_umma,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
             "peak_source": which, "flop_per_step": umma_flop, "gemm_ms_per_step": umma_ms,
             "gemm_share_of_step": umma_ms / step_ms if step_ms else None,

@@ -1,5 +1,6 @@
 // extern "C" entry points of libgoat_sm100 (see include/goat_sm100.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -13,6 +14,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GOAT_PDL");
+    v = (e && *e == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 bool gemm_umma_eligible(const goat_gemm_args& a);

@@ -171,6 +171,8 @@ attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                 // setup above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   constexpr int FMT = UmmaFmt<T>::value;
   constexpr uint32_t COL_O = 0, COL_S = 64;
   const int n_local = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -350,6 +352,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                 // setup above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   constexpr int FMT = UmmaFmt<T>::value;
   constexpr uint32_t COL_DV = 0, COL_DK = 64, COL_DQ = 128, COL_S = 192, COL_DP = 320;
   const int n_local = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -567,7 +571,7 @@ int fwd_launch(const goat_attn_args* a, cudaStream_t st) {
   PArgs t;
   fill(a, &t);
   const int grid = t.n_items < num_sms() ? t.n_items : num_sms();
-  attn_fwd_pipe_kernel<T><<<grid, P_THREADS, F_SMEM, st>>>(tq, tk, tv, t);
+  GOAT_CUDA(launch_pdl(attn_fwd_pipe_kernel<T>, dim3(grid), dim3(P_THREADS), (size_t)F_SMEM, st, tq, tk, tv, t));
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
@@ -589,7 +593,7 @@ int bwd_launch(const goat_attn_args* a, cudaStream_t st) {
   PArgs t;
   fill(a, &t);
   const int grid = t.n_items < num_sms() ? t.n_items : num_sms();
-  attn_bwd_pipe_kernel<T><<<grid, P_THREADS, B_SMEM, st>>>(tq, tk, tv, tg, t);
+  GOAT_CUDA(launch_pdl(attn_bwd_pipe_kernel<T>, dim3(grid), dim3(P_THREADS), (size_t)B_SMEM, st, tq, tk, tv, tg, t));
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

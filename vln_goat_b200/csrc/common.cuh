@@ -203,6 +203,33 @@ __device__ __forceinline__ float epi_apply(const EpiParams& ep, int m, int n, fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Kernels launched through launch_pdl() may become resident while the previous kernel
+// of the stream is still draining: their prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps its
+// tail, and pdl_wait() -- placed before the FIRST global-memory access -- blocks until the predecessor has completed
+// and its writes are visible.  pdl_launch_dependents() lets the successor do the same with this kernel.
+// A kernel that is launched with the attribute MUST execute pdl_wait() before touching global memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // GOAT_PDL=0 turns the launch attribute off (api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05  (sm_100a)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -175,6 +175,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -409,8 +411,7 @@ int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
   sc.num_tiles = mn * sc.splits;
   const int grid = sc.num_tiles < num_sms() ? sc.num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, a.M, a.N, a.K, sc);
-  GOAT_LAUNCH_CHECK();
+  GOAT_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, ep, a.M, a.N, a.K, sc));
   return GOAT_OK;
 }
 

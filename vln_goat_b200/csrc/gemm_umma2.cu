@@ -379,6 +379,8 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TL(7, 0);
+  pdl_wait();                 // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -530,8 +532,8 @@ int launch2(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
   sc.num_tiles = mn * sc.splits;
   const int clusters = sc.num_tiles < pairs ? sc.num_tiles : pairs;
-  kern<<<2 * clusters, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, a.M, a.N, a.K, sc, epi_mode_of(ep));
-  GOAT_LAUNCH_CHECK();
+  GOAT_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, ep, a.M, a.N, a.K, sc,
+                       epi_mode_of(ep)));
   return GOAT_OK;
 }
 

@@ -191,6 +191,8 @@ ln_fwd_vec_kernel(const void* __restrict__ x, const float* __restrict__ gamma, c
                   float* __restrict__ y32, void* __restrict__ y16, float* __restrict__ mean, float* __restrict__ rstd,
                   int M) {
   constexpr int H = NV * 128;
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= M) return;
@@ -237,6 +239,8 @@ ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, cons
                   int rows_per_cta) {
   constexpr int H = NV * 128;
   extern __shared__ float sacc[];  // [4 warps][3][H]
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 ag[NV], ab[NV], ac[NV], gm[NV];
 #pragma unroll
@@ -321,6 +325,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_finalize_vec_kernel(const float* __restrict__ partial, int nparts, int H, float* dgamma, float* dbeta,
                            float* dcolsum) {
   __shared__ float red[8][33];
+  pdl_wait();
+  pdl_launch_dependents();
   const int k = blockIdx.y;
   float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dcolsum);
   if (!out) return;
@@ -358,6 +364,8 @@ inline int ln_bwd_parts(int M) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const void* __restrict__ x, int M, int N, int ld, int rows_per_cta, float* __restrict__ partial) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= N) return;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -366,6 +374,8 @@ colsum_partial_kernel(const void* __restrict__ x, int M, int N, int ld, int rows
   partial[(size_t)blockIdx.y * N + c] = s;
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nparts, int N, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   float s = 0.f;
@@ -427,7 +437,7 @@ extern "C" int goat_layernorm_fwd(const void* x, int x_dtype, const float* gamma
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (H == 768 && aligned16(x) && (!y32 || aligned16(y32)) && (!y16 || aligned16(y16)) && aligned16(gamma) && aligned16(beta)) {
     dim3 g8((M + 7) / 8);
-#define LN_FWDV(TX, TY) ln_fwd_vec_kernel<TX, TY, 6><<<g8, 256, 0, st>>>(x, gamma, beta, eps, y32, y16, mean, rstd, M)
+#define LN_FWDV(TX, TY) GOAT_CUDA(launch_pdl(ln_fwd_vec_kernel<TX, TY, 6>, g8, dim3(256), (size_t)0, st, x, gamma, beta, eps, y32, y16, mean, rstd, M))
     const bool yh8 = (y16_dtype == GOAT_F16);
     if (x_dtype == GOAT_F32) { if (yh8) LN_FWDV(float, __half); else LN_FWDV(float, __nv_bfloat16); }
     else if (x_dtype == GOAT_F16) { if (yh8) LN_FWDV(__half, __half); else LN_FWDV(__half, __nv_bfloat16); }
@@ -479,8 +489,9 @@ extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, c
       GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_vec_kernel<TX, TD, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, VSMEM)); \
       cfgv = true;                                                                                                    \
     }                                                                                                                 \
-    ln_bwd_vec_kernel<TX, TD, 6><<<vparts, 128, VSMEM, st>>>(dy, x, gamma, mean, rstd, dres, dx32, dx16, drop_p,      \
-        drop_seed, reinterpret_cast<const unsigned long long*>(drop_seed_ptr), partial, M, vrows);                    \
+    GOAT_CUDA(launch_pdl(ln_bwd_vec_kernel<TX, TD, 6>, dim3(vparts), dim3(128), (size_t)VSMEM, st, dy, x, gamma, mean, rstd, \
+        dres, dx32, dx16, drop_p, (unsigned long long)drop_seed,                                                      \
+        reinterpret_cast<const unsigned long long*>(drop_seed_ptr), partial, M, vrows));                              \
   } while (0)
 #define LN_BWDV_X(TX)                                                     \
   do {                                                                    \
@@ -495,7 +506,8 @@ extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, c
 #undef LN_BWDV_X
 #undef LN_BWDV
     GOAT_LAUNCH_CHECK();
-    ln_bwd_finalize_vec_kernel<<<dim3(768 / 32, 3), 256, 0, st>>>(partial, vparts, H, dgamma, dbeta, dcolsum);
+    GOAT_CUDA(launch_pdl(ln_bwd_finalize_vec_kernel, dim3(768 / 32, 3), dim3(256), (size_t)0, st, (const float*)partial, vparts, H,
+                         dgamma, dbeta, dcolsum));
     GOAT_LAUNCH_CHECK();
     return GOAT_OK;
   }
@@ -547,12 +559,12 @@ extern "C" int goat_colsum(const void* x, int dtype, int M, int N, int ld, float
   const int rows_per_cta = (M + parts - 1) / parts;
   dim3 grid((N + 255) / 256, parts);
   float* partial = reinterpret_cast<float*>(workspace);
-  if (dtype == GOAT_F32) colsum_partial_kernel<float><<<grid, 256, 0, st>>>(x, M, N, ld, rows_per_cta, partial);
-  else if (dtype == GOAT_F16) colsum_partial_kernel<__half><<<grid, 256, 0, st>>>(x, M, N, ld, rows_per_cta, partial);
-  else if (dtype == GOAT_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, M, N, ld, rows_per_cta, partial);
+  if (dtype == GOAT_F32) GOAT_CUDA(launch_pdl(colsum_partial_kernel<float>, grid, dim3(256), (size_t)0, st, x, M, N, ld, rows_per_cta, partial));
+  else if (dtype == GOAT_F16) GOAT_CUDA(launch_pdl(colsum_partial_kernel<__half>, grid, dim3(256), (size_t)0, st, x, M, N, ld, rows_per_cta, partial));
+  else if (dtype == GOAT_BF16) GOAT_CUDA(launch_pdl(colsum_partial_kernel<__nv_bfloat16>, grid, dim3(256), (size_t)0, st, x, M, N, ld, rows_per_cta, partial));
   else GOAT_CHECK(false, "goat_colsum: bad dtype");
   GOAT_LAUNCH_CHECK();
-  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, parts, N, out);
+  GOAT_CUDA(launch_pdl(colsum_final_kernel, dim3((N + 127) / 128), dim3(128), (size_t)0, st, (const float*)partial, parts, N, out));
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

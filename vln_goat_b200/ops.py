@@ -12,7 +12,8 @@ from ._lib import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, 
 
 # kernels launched by this library since import (bench.py reports the per-step delta as gpu_launches)
 LAUNCHES = [0]
-# when set to a list, every gemm() call appends (M, N, K, a_mn, b_mn, dtype code, ran_on_simt) -- bench.py's roofline pass
+# when set to a list, every gemm() call appends (M, N, K, a_mn, b_mn, dtype code, ran_on_simt, accumulate, act, has_bias,
+# has_res, out_is_fp32, has_dropout, has_out2) -- bench.py's roofline pass re-times exactly these launches
 GEMM_LOG = None
 
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
@@ -96,7 +97,8 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
     LAUNCHES[0] += 1
     if GEMM_LOG is not None:
         umma = a.dtype != F32 and K >= 16 and K % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and not force_simt
-        GEMM_LOG.append((M, N, K, int(a_mn), int(b_mn), a.dtype, int(not umma)))
+        GEMM_LOG.append((M, N, K, int(a_mn), int(b_mn), a.dtype, int(not umma), int(accumulate), int(act), int(bias is not None),
+                         int(res is not None), int(out.dtype == torch.float32), int(drop_p > 0.0), int(out2 is not None)))
     return out
 
 
