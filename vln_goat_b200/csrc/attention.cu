@@ -60,8 +60,9 @@ __device__ __forceinline__ float score_bias(const goat_attn_args& a, int b, int 
 
 __device__ __forceinline__ float drop_scale(const goat_attn_args& a, int b, int h, int qi, int kj) {
   if (a.drop_p <= 0.f) return 1.f;
-  const unsigned long long idx = (((unsigned long long)b * a.heads + h) * a.Nq + qi) * (unsigned long long)a.Nk + kj;
-  return rand_uniform(eff_seed(a.drop_seed, reinterpret_cast<const unsigned long long*>(a.drop_seed_ptr)), idx) >= a.drop_p ? 1.f / (1.f - a.drop_p) : 0.f;
+  const uint32_t rowkey = attn_drop_rowkey(eff_seed(a.drop_seed, reinterpret_cast<const unsigned long long*>(a.drop_seed_ptr)),
+                                           b, a.heads, h, a.Nq, qi);
+  return attn_drop_keep(rowkey, kj, drop_thr16(a.drop_p)) ? 1.f / (1.f - a.drop_p) : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

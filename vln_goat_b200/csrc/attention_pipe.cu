@@ -124,11 +124,15 @@ __device__ __forceinline__ void store_global_row32(T* dst, const uint32_t (&v)[3
   }
 }
 
-// same element index as the SIMT kernels (attention.cu) and attention_tc.cu: masks agree across all paths
-__device__ __forceinline__ float drop_mul(const PArgs& p, unsigned long long seed, int b, int h, int qi, int kj) {
-  const unsigned long long idx =
-      (((unsigned long long)b * p.heads + h) * p.Nq + qi) * (unsigned long long)p.Nk + kj;
-  return rand_uniform(seed, idx) >= p.drop_p ? 1.f / (1.f - p.drop_p) : 0.f;
+// same (row key, key pair) hashing as the SIMT kernels (attention.cu) and attention_tc.cu: masks agree across all paths.
+// 16 consecutive keys starting at k0 (a multiple of 16): 8 pair hashes
+__device__ __forceinline__ void drop_mul16(float (&v)[16], uint32_t rowkey, int k0, uint32_t thr16, float scale) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const uint32_t r = attn_drop_pair(rowkey, k0 + j);
+    v[j] = (r & 0xFFFFu) >= thr16 ? v[j] * scale : 0.f;
+    v[j + 1] = (r >> 16) >= thr16 ? v[j + 1] * scale : 0.f;
+  }
 }
 
 __device__ __forceinline__ float load_kml(const PArgs& p, int b, int key) {
@@ -233,6 +237,8 @@ attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float sl2 = p.scale * LOG2E;
     const bool drop = p.drop_p > 0.f;
     const unsigned long long seed = drop ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
+    const uint32_t thr16 = drop_thr16(p.drop_p);
+    const float keep_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
     if (n_local > 0 && cidx < 128) kml[cidx] = load_kml(p, (int)blockIdx.x / p.heads, cidx);
     compute_bar();
     for (int i = 0; i < n_local; ++i) {
@@ -281,10 +287,7 @@ attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             l += e;
             pv[j] = e;
           }
-          if (drop) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pv[j] *= drop_mul(p, seed, b, h, r, kb * 16 + j);
-          }
+          if (drop) drop_mul16(pv, attn_drop_rowkey(seed, b, p.heads, h, p.Nq, r), kb * 16, thr16, keep_scale);
           store_row16<T>(sP, r, kb * 16, pv);
         }
       }
@@ -429,6 +432,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float sl2 = p.scale * LOG2E;
     const bool drop = p.drop_p > 0.f;
     const unsigned long long seed = drop ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
+    const uint32_t thr16 = drop_thr16(p.drop_p);
+    const float keep_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
     float lse_next = 0.f;
     if (n_local > 0) {
       const int b0 = (int)blockIdx.x / p.heads, h0 = (int)blockIdx.x % p.heads;
@@ -473,10 +478,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             pk[t][j] = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, kv[j]) - lse);
             pt[j] = pk[t][j];
           }
-          if (drop) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pt[j] *= drop_mul(p, seed, b, h, r, kb * 16 + j);
-          }
+          if (drop) drop_mul16(pt, attn_drop_rowkey(seed, b, p.heads, h, p.Nq, r), kb * 16, thr16, keep_scale);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             ck[t][j] = pt[j] * __uint_as_float(rp[j]);

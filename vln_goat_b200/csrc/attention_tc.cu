@@ -96,9 +96,8 @@ __device__ __forceinline__ void store_global_row64(T* dst, const float* v, float
 }
 
 __device__ __forceinline__ float drop_mul(const TcArgs& p, unsigned long long seed, int b, int h, int qi, int kj) {
-  const unsigned long long idx =
-      (((unsigned long long)b * p.heads + h) * p.Nq + qi) * (unsigned long long)p.Nk + kj;
-  return rand_uniform(seed, idx) >= p.drop_p ? 1.f / (1.f - p.drop_p) : 0.f;
+  const uint32_t rowkey = attn_drop_rowkey(seed, b, p.heads, h, p.Nq, qi);
+  return attn_drop_keep(rowkey, kj, drop_thr16(p.drop_p)) ? 1.f / (1.f - p.drop_p) : 0.f;
 }
 
 struct Smem {

@@ -100,19 +100,55 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// counter-based uniform in [0,1): a 32-bit multiply-xorshift hash of (seed, index).  Used for dropout masks so
-// the backward pass can regenerate the forward mask from (seed, element index) without storing it.  Seven integer
-// instructions per element (the 64-bit splitmix this replaced cost ~4x that in the GEMM / attention epilogues);
-// statistical quality is ample for Bernoulli masks (tests check the keep rate and mask equality across kernels).
-__device__ __forceinline__ float rand_uniform(unsigned long long seed, unsigned long long idx) {
-  unsigned int x = (unsigned int)idx * 0x9E3779B1u + (unsigned int)seed;
-  x ^= (unsigned int)(idx >> 32) * 0x85EBCA6Bu + (unsigned int)(seed >> 32);
-  x ^= x >> 16;
-  x *= 0x7FEB352Du;
-  x ^= x >> 15;
-  x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  return (float)(x >> 8) * (1.0f / 16777216.0f);
+// Dropout masks are never stored: every kernel regenerates them from (seed, element index), so forward and backward
+// (and the tcgen05 and SIMT variants of a kernel) agree by construction.  ONE 32-bit hash serves the element PAIR
+// (2k, 2k+1) -- 16 random bits each -- and an element is kept iff its 16 bits >= round(p * 65536) (p is realised to
+// within 8e-6).  The hash is two rounds of multiply-and-fold (32x32->64-bit product, high word xor low word): about
+// 5 integer instructions per pair once the per-row part is hoisted.
+__device__ __forceinline__ uint32_t mulfold(uint32_t a, uint32_t b) {
+  const unsigned long long r = (unsigned long long)a * (unsigned long long)b;
+  return (uint32_t)(r >> 32) ^ (uint32_t)r;
+}
+__device__ __forceinline__ uint32_t drop_thr16(float p) { return (uint32_t)__float2uint_rn(p * 65536.0f); }
+// 32 random bits for pair `pair_idx` of a linearly indexed tensor (GEMM epilogue, LayerNorm backward, casts)
+__device__ __forceinline__ uint32_t drop_hash(unsigned long long seed, unsigned long long pair_idx) {
+  const uint32_t x = mulfold((uint32_t)pair_idx ^ (uint32_t)seed ^ 0x9E3779B1u,
+                             (uint32_t)(pair_idx >> 32) ^ (uint32_t)(seed >> 32) ^ 0x85EBCA6Bu);
+  return mulfold(x ^ 0x7FEB352Du, 0x846CA68Bu);
+}
+// keep decision of one element (scalar paths)
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, uint32_t thr16) {
+  const uint32_t r = drop_hash(seed, idx >> 1);
+  return ((idx & 1ull) ? (r >> 16) : (r & 0xFFFFu)) >= thr16;
+}
+// keep decisions of elements idx, idx+1 (idx even)
+__device__ __forceinline__ void drop_keep2(unsigned long long seed, unsigned long long idx_even, uint32_t thr16, bool& k0, bool& k1) {
+  const uint32_t r = drop_hash(seed, idx_even >> 1);
+  k0 = (r & 0xFFFFu) >= thr16;
+  k1 = (r >> 16) >= thr16;
+}
+// 4 consecutive elements starting at idx (idx % 4 == 0): v[j] = keep ? v[j] * scale : 0
+__device__ __forceinline__ void drop_apply4(float (&v)[4], unsigned long long seed, unsigned long long idx, uint32_t thr16, float scale) {
+  bool k0, k1, k2, k3;
+  drop_keep2(seed, idx, thr16, k0, k1);
+  drop_keep2(seed, idx + 2, thr16, k2, k3);
+  v[0] = k0 ? v[0] * scale : 0.0f;
+  v[1] = k1 ? v[1] * scale : 0.0f;
+  v[2] = k2 ? v[2] * scale : 0.0f;
+  v[3] = k3 ? v[3] * scale : 0.0f;
+}
+// Attention-probability dropout: a 32-bit key per (seed, batch, head, query row), then one hash per key PAIR (kj, kj+1),
+// kj even.  Shared by the SIMT, chunked tcgen05 and pipelined tcgen05 attention kernels.
+__device__ __forceinline__ uint32_t attn_drop_rowkey(unsigned long long seed, int b, int heads, int h, int Nq, int qi) {
+  return drop_hash(seed, ((unsigned long long)b * heads + h) * (unsigned long long)Nq + qi);
+}
+__device__ __forceinline__ uint32_t attn_drop_pair(uint32_t rowkey, int kj_even) {
+  const uint32_t x = mulfold(rowkey ^ ((uint32_t)(kj_even >> 1) * 0x9E3779B1u), 0x85EBCA6Bu ^ rowkey);
+  return mulfold(x ^ 0x7FEB352Du, 0x846CA68Bu);
+}
+__device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int kj, uint32_t thr16) {
+  const uint32_t r = attn_drop_pair(rowkey, kj & ~1);
+  return ((kj & 1) ? (r >> 16) : (r & 0xFFFFu)) >= thr16;
 }
 
 // erf-GELU and its derivative for the 16-bit tensor-core epilogues: Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7,
@@ -194,9 +230,9 @@ __device__ __forceinline__ float epi_apply(const EpiParams& ep, int m, int n, fl
     v = tanhf(v);
   }
   if (ep.drop_p > 0.0f) {
-    const float u = rand_uniform(eff_seed(ep.drop_seed, ep.drop_seed_ptr),
-                                 (unsigned long long)m * (unsigned long long)ep.ldc + n);
-    v = (u >= ep.drop_p) ? v * (1.0f / (1.0f - ep.drop_p)) : 0.0f;
+    const bool keep = drop_keep(eff_seed(ep.drop_seed, ep.drop_seed_ptr),
+                                (unsigned long long)m * (unsigned long long)ep.ldc + n, drop_thr16(ep.drop_p));
+    v = keep ? v * (1.0f / (1.0f - ep.drop_p)) : 0.0f;
   }
   if (ep.res) v += ep.res[(size_t)m * ep.ldres + n];
   return v;

@@ -97,14 +97,8 @@ __device__ __forceinline__ void epi_store4(const EpiParams& ep, int m, int n, fl
     for (int j = 0; j < 4; ++j)
       v[j] = (ep.act == GOAT_ACT_DGELU) ? v[j] * dgelu_fast(z[j]) : (z[j] > 0.0f ? v[j] : 0.0f);
   }
-  if (ep.drop_p > 0.0f) {
-    const float keep = 1.0f / (1.0f - ep.drop_p);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float u = rand_uniform(seed, (unsigned long long)m * (unsigned long long)ep.ldc + n + j);
-      v[j] = (u >= ep.drop_p) ? v[j] * keep : 0.0f;
-    }
-  }
+  if (ep.drop_p > 0.0f)   // vector path: ldc % 4 == 0 and n % 4 == 0, so the element index is a multiple of 4
+    drop_apply4(v, seed, (unsigned long long)m * (unsigned long long)ep.ldc + n, drop_thr16(ep.drop_p), 1.0f / (1.0f - ep.drop_p));
   if (ep.res) {
     const float4 b = *reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.ldres + n);
     v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;

@@ -162,15 +162,10 @@ __device__ __forceinline__ void prefetch_patch(const EpiParams& ep, int mrow0, i
   }
 }
 
-__device__ __forceinline__ void drop4(float (&v)[4], float drop_p, float keep, unsigned long long seed, unsigned long long idx) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = (rand_uniform(seed, idx + j) >= drop_p) ? v[j] * keep : 0.0f;
-}
-
 // 4 consecutive outputs (row m, columns n..n+3) of a full, aligned patch
 template <typename T, int MODE>
 __device__ __forceinline__ void epi_out4(const EpiParams& ep, int m, int n, float4 acc, float4 b4, const Pre<MODE>& pre, int i,
-                                         float keep, unsigned long long seed) {
+                                         float keep, uint32_t thr16, unsigned long long seed) {
   float v[4] = {acc.x * ep.alpha, acc.y * ep.alpha, acc.z * ep.alpha, acc.w * ep.alpha};
   if constexpr (MODE == EPI_ACC) {
     atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldc + n),
@@ -195,7 +190,7 @@ __device__ __forceinline__ void epi_out4(const EpiParams& ep, int m, int n, floa
     v[0] *= dgelu_fast(a.x); v[1] *= dgelu_fast(a.y); v[2] *= dgelu_fast(b.x); v[3] *= dgelu_fast(b.y);
   }
   if constexpr (MODE != EPI_T16) {
-    if (ep.drop_p > 0.0f) drop4(v, ep.drop_p, keep, seed, (unsigned long long)m * (unsigned long long)ep.ldc + n);
+    if (ep.drop_p > 0.0f) drop_apply4(v, seed, (unsigned long long)m * (unsigned long long)ep.ldc + n, thr16, keep);
   }
   if constexpr (MODE == EPI_RES32) {
     if (ep.res) { v[0] += pre.res[i].x; v[1] += pre.res[i].y; v[2] += pre.res[i].z; v[3] += pre.res[i].w; }
@@ -257,6 +252,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
   const int c4 = (cx.lane & 7) * 4;    // column offset of this lane's float4
   const unsigned long long seed = ep.drop_p > 0.0f ? eff_seed(ep.drop_seed, ep.drop_seed_ptr) : 0ull;
   const float keep = ep.drop_p > 0.0f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+  const uint32_t thr16 = drop_thr16(ep.drop_p);
   float* patch = cx.patch;
 
   int local = 0;
@@ -320,7 +316,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
           for (int i = 0; i < 8; ++i) acc[i] = *reinterpret_cast<const float4*>(patch + (i * 4 + rl) * PATCH_LD + c4);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            epi_out4<T, MODE>(ep, mrow0 + i * 4 + rl, nc + c4, acc[i], b4, cur, i, keep, seed);
+            epi_out4<T, MODE>(ep, mrow0 + i * 4 + rl, nc + c4, acc[i], b4, cur, i, keep, thr16, seed);
         } else {
           epi_patch_scalar<T>(ep, patch, mrow0, nc, M, N, rl, c4);
         }

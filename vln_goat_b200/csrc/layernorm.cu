@@ -112,7 +112,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x, const fl
           if (dx32) dx32[(size_t)row * H + c] = d + (dres ? dres[(size_t)row * H + c] : 0.f);
           float dm = d;
           if (drop_p > 0.f)
-            dm = rand_uniform(drop_seed, (unsigned long long)row * (unsigned long long)H + c) >= drop_p ? d * keep : 0.f;
+            dm = drop_keep(drop_seed, (unsigned long long)row * (unsigned long long)H + c, drop_thr16(drop_p)) ? d * keep : 0.f;
           if (dx16) {
             const TD q = from_f<TD>(dm);
             reinterpret_cast<TD*>(dx16)[(size_t)row * H + c] = q;
@@ -289,10 +289,9 @@ ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, cons
       }
       float4 dm = d;
       if (drop_p > 0.f) {
-        dm.x = rand_uniform(drop_seed, (unsigned long long)o + 0) >= drop_p ? d.x * keep : 0.f;
-        dm.y = rand_uniform(drop_seed, (unsigned long long)o + 1) >= drop_p ? d.y * keep : 0.f;
-        dm.z = rand_uniform(drop_seed, (unsigned long long)o + 2) >= drop_p ? d.z * keep : 0.f;
-        dm.w = rand_uniform(drop_seed, (unsigned long long)o + 3) >= drop_p ? d.w * keep : 0.f;
+        float v4[4] = {d.x, d.y, d.z, d.w};
+        drop_apply4(v4, drop_seed, (unsigned long long)o, drop_thr16(drop_p), keep);
+        dm = make_float4(v4[0], v4[1], v4[2], v4[3]);
       }
       if (dx16) {
         st4<TD>(dx16, o, dm);
@@ -399,7 +398,7 @@ __global__ void cast_kernel(const S* __restrict__ src, Dt* __restrict__ dst, lon
     const unsigned long long seed = eff_seed(drop_seed_, drop_seed_ptr);
     const float keep = 1.f / (1.f - drop_p);
     for (; i < e; ++i)
-      dst[i] = from_f<Dt>(rand_uniform(seed, (unsigned long long)i) >= drop_p ? to_f<S>(src[i]) * keep : 0.f);
+      dst[i] = from_f<Dt>(drop_keep(seed, (unsigned long long)i, drop_thr16(drop_p)) ? to_f<S>(src[i]) * keep : 0.f);
   } else {
     for (; i < e; ++i) dst[i] = from_f<Dt>(to_f<S>(src[i]));
   }
