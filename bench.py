@@ -219,7 +219,7 @@ def run_goat(args):
 
     def loss_fn(txt, tm, vp, vm):
         t, v = model(txt, tm, vp, vm)
-        return 0.5 * (t * t).mean() + 0.5 * (v * v).mean()
+        return workloads.c2_loss(t, v)
 
     host = [tuple(t.pin_memory() for t in b) for b in make_batches(4, B, seed=1000 + rank)]
     devb = [tuple(t.to(dev) for t in b) for b in host]

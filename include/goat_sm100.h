@@ -164,6 +164,10 @@ int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float*
 /* column sum: out[n] = sum_m x[m*ld + n]  (bias gradients).  workspace: goat_colsum_workspace_bytes(M,N) */
 size_t goat_colsum_workspace_bytes(int M, int N);
 int goat_colsum(const void* x, int dtype, int M, int N, int ld, float* out, void* workspace, goat_stream_t stream);
+/* out[n] += sum_m x[m,n] in ONE kernel with fp32 atomics (out zero-initialised or holding an earlier partial sum, e.g. a
+ * flat-gradient view the optimizer cleared).  N and ld multiples of 16/sizeof(dtype) elements, x 16-byte aligned.
+ * Same reference sites as goat_colsum (bias gradients of every nn.Linear on the path). */
+int goat_colsum_acc(const void* x, int dtype, int M, int N, int ld, float* out, goat_stream_t stream);
 
 /* dtype conversion of n contiguous elements (fp32 master weights -> 16-bit operands, activations in/out) */
 int goat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, goat_stream_t stream);

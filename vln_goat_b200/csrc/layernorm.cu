@@ -388,6 +388,48 @@ inline int colsum_parts(int M) {
   return parts;
 }
 
+// One-kernel column sums accumulated with fp32 atomics into a zero-initialised (or partially filled) destination -- the
+// bias gradients land directly in the flat gradient buffer, which the optimizer kernel clears every step.
+// Block = 8 warps; a warp reads whole 512-byte row segments (16 bytes per lane), blockIdx.x picks the 32*VEC-column
+// group, blockIdx.y the row chunk; per-warp register sums -> smem -> one atomic per column and block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_atomic_kernel(const T* __restrict__ x, int M, int N, int ld, int rows_per_cta, float* __restrict__ out) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float red[8][32 * VEC + 1];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * (32 * VEC) + lane * VEC;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (c0 < N) {   // N % VEC == 0: a lane's VEC columns are all in range or all out
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const uint4 w = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + c0);
+      if constexpr (sizeof(T) == 4) {
+        acc[0] += __uint_as_float(w.x); acc[1] += __uint_as_float(w.y); acc[2] += __uint_as_float(w.z); acc[3] += __uint_as_float(w.w);
+      } else {
+        const float2 a = unpack2<T>(w.x), b = unpack2<T>(w.y), c = unpack2<T>(w.z), d = unpack2<T>(w.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) red[warp][lane * VEC + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int col = blockIdx.x * (32 * VEC) + c;
+    if (col < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][c];
+      atomicAdd(out + col, t);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <typename S, typename Dt>
 __global__ void cast_kernel(const S* __restrict__ src, Dt* __restrict__ dst, long long n, float drop_p,
@@ -565,6 +607,31 @@ extern "C" int goat_colsum(const void* x, int dtype, int M, int N, int ld, float
   GOAT_LAUNCH_CHECK();
   GOAT_CUDA(launch_pdl(colsum_final_kernel, dim3((N + 127) / 128), dim3(128), (size_t)0, st, (const float*)partial, parts, N, out));
   GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" int goat_colsum_acc(const void* x, int dtype, int M, int N, int ld, float* out, goat_stream_t stream) {
+  GOAT_CHECK(x && out, "goat_colsum_acc: null argument");
+  GOAT_CHECK(dtype == GOAT_F32 || dtype == GOAT_F16 || dtype == GOAT_BF16, "goat_colsum_acc: bad dtype");
+  const int vec = 16 / dtype_size(dtype);
+  GOAT_CHECK(N > 0 && ld >= N && (N % vec) == 0 && (ld % vec) == 0 && aligned16(x),
+             "goat_colsum_acc: N and ld must be multiples of %d and x 16-byte aligned", vec);
+  if (M <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int gx = (N + 32 * vec - 1) / (32 * vec);
+  int gy = (2 * 148 + gx - 1) / gx;                 // about two CTAs per SM in total
+  const int max_gy = (M + 15) / 16;                 // at least 16 rows (2 per warp) per CTA
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  const int rows_per_cta = (M + gy - 1) / gy;
+  gy = (M + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid(gx, gy);
+  if (dtype == GOAT_F32)
+    GOAT_CUDA(launch_pdl(colsum_atomic_kernel<float>, grid, dim3(256), (size_t)0, st, (const float*)x, M, N, ld, rows_per_cta, out));
+  else if (dtype == GOAT_F16)
+    GOAT_CUDA(launch_pdl(colsum_atomic_kernel<__half>, grid, dim3(256), (size_t)0, st, (const __half*)x, M, N, ld, rows_per_cta, out));
+  else
+    GOAT_CUDA(launch_pdl(colsum_atomic_kernel<__nv_bfloat16>, grid, dim3(256), (size_t)0, st, (const __nv_bfloat16*)x, M, N, ld, rows_per_cta, out));
   return GOAT_OK;
 }
 

@@ -110,7 +110,8 @@ def _bgrad(params, dy_c):
     """db = column sums of dY."""
     if params[0] is None:
         return (None,) * len(params)
-    return _grad_into(params, lambda out, acc: ops.colsum(dy_c, out=out), False)
+    # one atomic-accumulate kernel straight into the (optimizer-zeroed) flat gradient view, or into fresh zeros
+    return _grad_into(params, lambda out, acc: ops.colsum(dy_c, out=out, accumulate=True), True, always_acc=True)
 
 
 def _vgrad(param, t):
@@ -162,6 +163,7 @@ class AttnBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x32, x16, kv32, kv16, kmask, bias, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, Wqkv_c, bqkv,
                 Wo_c, cfg):
+        ctx.set_materialize_grads(False)   # no zero-filled gradient for the non-differentiable 16-bit copy
         H = x32.shape[1]
         cdt = cfg.cdt
         xc = _c(x32, x16, cdt)
@@ -200,7 +202,7 @@ class AttnBlockFn(torch.autograd.Function):
         cdt = cfg.cdt
         H = pre.shape[1]
         B, Nq, Nk = cfg.B, cfg.Nq, cfg.Nk
-        dy32 = dy32.contiguous()
+        dy32 = torch.zeros_like(pre) if dy32 is None else dy32.contiguous()
         # LN backward: dpre32 feeds the residual path, dpre_c (dropout-masked) feeds the out-proj GEMMs
         dpre32, dpre_c, dgamma, dbeta, dbo = _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, cfg.hid_p, cfg.seed + 1,
                                                            cfg.seed_ptr, gamma_p, beta_p, bo)
@@ -245,6 +247,7 @@ class FFNBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x32, x16, W1, b1, W2, b2, gamma, beta, W1_c, W2_c, cfg):
+        ctx.set_materialize_grads(False)
         cdt = cfg.cdt
         xc = _c(x32, x16, cdt)
         M = xc.shape[0]
@@ -267,7 +270,8 @@ class FFNBlockFn(torch.autograd.Function):
         xc, z, h, pre, mean, rstd, W1_c, W2_c, gamma = ctx.saved_tensors
         cdt = cfg.cdt
         W1, b1, W2, b2, gamma_p, beta_p = ctx.params
-        dpre32, dpre_c, dgamma, dbeta, db2 = _ln_bwd_split(dy32.contiguous(), pre, gamma, mean, rstd, cdt, cfg.hid_p,
+        dy32 = torch.zeros_like(pre) if dy32 is None else dy32.contiguous()
+        dpre32, dpre_c, dgamma, dbeta, db2 = _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, cfg.hid_p,
                                                            cfg.seed, cfg.seed_ptr, gamma_p, beta_p, b2)
         dW2, = _wgrad((W2,), dpre_c, h)                                                      # [H,F]
         dz = ops.gemm(dpre_c, W2_c, b_mn=True, act=ops.ACT_DGELU, aux_in=z, out_dtype=cdt)   # [M,F]
@@ -401,6 +405,7 @@ class LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x32, gamma, beta, eps, cdt):
+        ctx.set_materialize_grads(False)
         y32, y16, mean, rstd = ops.layernorm_fwd(x32, gamma, beta, eps, True, _d16(cdt))
         ctx.params = (gamma, beta)
         ctx.save_for_backward(x32, gamma, mean, rstd)
@@ -411,6 +416,7 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _d16):
         x32, gamma, mean, rstd = ctx.saved_tensors
+        dy = torch.zeros_like(x32) if dy is None else dy
         dx32, _, dg, db, _ = _ln_bwd(dy.contiguous(), x32, gamma, mean, rstd, None, None, 0.0, 0, None, ctx.params[0],
                                      ctx.params[1])
         return dx32, dg, db, None, None

@@ -211,15 +211,24 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None
     return dx32, dx16, dgamma, dbeta, dcol
 
 
-def colsum(x, out=None):
-    """x [M,N] (unit inner stride) -> fp32 [N]"""
+def colsum(x, out=None, accumulate=False):
+    """x [M,N] (unit inner stride) -> fp32 [N].  accumulate=True: out += column sums in one kernel (fp32 atomics; out
+    zero-initialised or holding an earlier partial sum); a fresh zeroed tensor when out is None."""
     _req_cuda(x, out)
     ld = _rowmajor2d(x, "x")
     M, N = x.shape
     if out is None:
-        out = torch.empty((N,), device=x.device, dtype=torch.float32)
+        out = (torch.zeros if accumulate else torch.empty)((N,), device=x.device, dtype=torch.float32)
     elif out.dtype != torch.float32 or out.numel() != N or not out.is_contiguous():
         raise ValueError("colsum: out must be contiguous fp32 [N]")
+    if accumulate:
+        vec = 16 // x.element_size()
+        if N % vec == 0 and ld % vec == 0 and x.data_ptr() % 16 == 0:
+            _lib.check(_lib.lib().goat_colsum_acc(_p(x), dt(x), M, N, ld, _p(out), _stream()), "goat_colsum_acc")
+            LAUNCHES[0] += 1
+            return out
+        out.add_(colsum(x))     # odd widths (1-wide heads, 7/14-wide position features): two-kernel path
+        return out
     ws = torch.empty((_lib.lib().goat_colsum_workspace_bytes(M, N),), device=x.device, dtype=torch.uint8)
     _lib.check(_lib.lib().goat_colsum(_p(x), dt(x), M, N, ld, _p(out), _p(ws), _stream()), "goat_colsum")
     LAUNCHES[0] += 2

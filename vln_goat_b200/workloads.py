@@ -6,9 +6,31 @@ LocalVPEncoder.encoder = CrossmodalEncoder (3 BertCrossLayers) with the [stop]+3
 queries and the text as keys/values (P/model/vilmodel_goat.py:563-564 and :399).  Parameter names
 follow the reference model (``lang_encoder.layer.N.*``, ``local_encoder.encoder.crossattention.N.*``).
 """
+import torch
 from torch import nn
 
 from . import modules as M
+
+
+class _HalfMeanSquare(torch.autograd.Function):
+    """0.5 * mean(x^2) as one dot product forward and one scaled copy backward (the plain torch expression costs eight
+    elementwise / reduction launches over the output streams per step)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xf = x.reshape(-1)
+        ctx.save_for_backward(x)
+        return torch.dot(xf, xf) * (0.5 / xf.numel())
+
+    @staticmethod
+    def backward(ctx, go):
+        x, = ctx.saved_tensors
+        return x * (go * (1.0 / x.numel()))
+
+
+def c2_loss(txt_out, vp_out):
+    """The synthetic objective of the C2 workload (oracle.goat_oracle.c2_loss): mean square of both output streams."""
+    return _HalfMeanSquare.apply(txt_out) + _HalfMeanSquare.apply(vp_out)
 
 
 class _LocalBranch(nn.Module):
