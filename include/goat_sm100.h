@@ -160,6 +160,13 @@ int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, const float*
                        const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype, float drop_p,
                        uint64_t drop_seed, const uint64_t* drop_seed_ptr, float* dgamma, float* dbeta, float* dcolsum,
                        void* workspace, int M, int H, goat_stream_t stream);
+/* Same backward, but dgamma / dbeta / dcolsum are ACCUMULATED into with vector fp32 atomics by the one kernel (no
+ * workspace, no finalize launch): pass zero-initialised vectors or flat-gradient views that already hold other
+ * contributions.  H must be 768 and every tensor 16-byte aligned, else GOAT_ERR_UNSUPPORTED. */
+int goat_layernorm_bwd_acc(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
+                           const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype, float drop_p,
+                           uint64_t drop_seed, const uint64_t* drop_seed_ptr, float* dgamma, float* dbeta,
+                           float* dcolsum, int M, int H, goat_stream_t stream);
 
 /* column sum: out[n] = sum_m x[m*ld + n]  (bias gradients).  workspace: goat_colsum_workspace_bytes(M,N) */
 size_t goat_colsum_workspace_bytes(int M, int N);

@@ -230,13 +230,16 @@ ln_fwd_vec_kernel(const void* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
-template <typename TX, typename TD, int NV>
+// ACC = false: per-CTA column partials [gridDim.x][3][H] for ln_bwd_finalize_vec_kernel (deterministic order).
+// ACC = true : the CTA totals are added straight into dgamma / dbeta / dcolsum with vector fp32 atomics (destinations
+//              zero-initialised or holding earlier contributions, e.g. flat-gradient views) -- no second kernel.
+template <typename TX, typename TD, int NV, bool ACC>
 __global__ void __launch_bounds__(128)
 ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                   float* __restrict__ dx32, void* __restrict__ dx16, float drop_p, unsigned long long drop_seed_,
                   const unsigned long long* __restrict__ drop_seed_ptr, float* __restrict__ partial, int M,
-                  int rows_per_cta) {
+                  int rows_per_cta, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   constexpr int H = NV * 128;
   extern __shared__ float sacc[];  // [4 warps][3][H]
   pdl_wait();
@@ -311,11 +314,25 @@ ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, cons
     *reinterpret_cast<float4*>(&sacc[(warp * 3 + 2) * H + c]) = ac[i];
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) {
-    float t = 0.f;
+  if constexpr (ACC) {
+    for (int e = threadIdx.x * 4; e < 3 * H; e += blockDim.x * 4) {
+      float4 t = *reinterpret_cast<const float4*>(&sacc[e]);
 #pragma unroll
-    for (int w = 0; w < 4; ++w) t += sacc[w * 3 * H + e];
-    partial[(size_t)blockIdx.x * 3 * H + e] = t;
+      for (int w = 1; w < 4; ++w) {
+        const float4 u = *reinterpret_cast<const float4*>(&sacc[w * 3 * H + e]);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      const int k = e / H, c = e - k * H;
+      float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dcolsum);
+      if (out) atomicAdd(reinterpret_cast<float4*>(out + c), t);
+    }
+  } else {
+    for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) t += sacc[w * 3 * H + e];
+      partial[(size_t)blockIdx.x * 3 * H + e] = t;
+    }
   }
 }
 
@@ -527,12 +544,13 @@ extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, c
   do {                                                                                                                \
     static bool cfgv = false;                                                                                         \
     if (!cfgv) {                                                                                                      \
-      GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_vec_kernel<TX, TD, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, VSMEM)); \
+      GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_vec_kernel<TX, TD, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VSMEM)); \
       cfgv = true;                                                                                                    \
     }                                                                                                                 \
-    GOAT_CUDA(launch_pdl(ln_bwd_vec_kernel<TX, TD, 6>, dim3(vparts), dim3(128), (size_t)VSMEM, st, dy, x, gamma, mean, rstd, \
+    GOAT_CUDA(launch_pdl(ln_bwd_vec_kernel<TX, TD, 6, false>, dim3(vparts), dim3(128), (size_t)VSMEM, st, dy, x, gamma, mean, rstd, \
         dres, dx32, dx16, drop_p, (unsigned long long)drop_seed,                                                      \
-        reinterpret_cast<const unsigned long long*>(drop_seed_ptr), partial, M, vrows));                              \
+        reinterpret_cast<const unsigned long long*>(drop_seed_ptr), partial, M, vrows, (float*)nullptr, (float*)nullptr, \
+        (float*)nullptr));                                                                                            \
   } while (0)
 #define LN_BWDV_X(TX)                                                     \
   do {                                                                    \
@@ -582,6 +600,52 @@ extern "C" int goat_layernorm_bwd(const float* dy, const void* x, int x_dtype, c
   GOAT_LAUNCH_CHECK();
   ln_bwd_finalize_kernel<<<(H + 127) / 128, 128, 0, st>>>(partial, parts, H, dgamma, dbeta, dcolsum);
   GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" int goat_layernorm_bwd_acc(const float* dy, const void* x, int x_dtype, const float* gamma, const float* mean,
+                                      const float* rstd, const float* dres, float* dx32, void* dx16, int dx16_dtype,
+                                      float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_ptr, float* dgamma,
+                                      float* dbeta, float* dcolsum, int M, int H, goat_stream_t stream) {
+  GOAT_CHECK(dy && x && gamma && mean && rstd, "goat_layernorm_bwd_acc: null argument");
+  GOAT_CHECK(!dx16 || dx16_dtype == GOAT_F16 || dx16_dtype == GOAT_BF16 || dx16_dtype == GOAT_F32,
+             "goat_layernorm_bwd_acc: bad dx16 dtype");
+  GOAT_CHECK(drop_p >= 0.f && drop_p < 1.f, "goat_layernorm_bwd_acc: drop_p out of range");
+  if (!(H == 768 && aligned16(dy) && aligned16(x) && aligned16(gamma) && (!dres || aligned16(dres)) &&
+        (!dx32 || aligned16(dx32)) && (!dx16 || aligned16(dx16)) && (!dgamma || aligned16(dgamma)) &&
+        (!dbeta || aligned16(dbeta)) && (!dcolsum || aligned16(dcolsum)))) {
+    set_error("goat_layernorm_bwd_acc: needs H == 768 and 16-byte aligned tensors (use goat_layernorm_bwd)");
+    return GOAT_ERR_UNSUPPORTED;
+  }
+  if (M <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int vparts = ln_bwd_vec_parts(M);
+  const int vrows = (M + vparts - 1) / vparts;
+  constexpr int VSMEM = 4 * 3 * 768 * 4;
+  const int ddv = dx16 ? dx16_dtype : GOAT_F16;
+#define LN_BWDA(TX, TD)                                                                                               \
+  do {                                                                                                                \
+    static bool cfga = false;                                                                                         \
+    if (!cfga) {                                                                                                      \
+      GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_vec_kernel<TX, TD, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VSMEM)); \
+      cfga = true;                                                                                                    \
+    }                                                                                                                 \
+    GOAT_CUDA(launch_pdl(ln_bwd_vec_kernel<TX, TD, 6, true>, dim3(vparts), dim3(128), (size_t)VSMEM, st, dy, x, gamma, mean, rstd, \
+        dres, dx32, dx16, drop_p, (unsigned long long)drop_seed,                                                      \
+        reinterpret_cast<const unsigned long long*>(drop_seed_ptr), (float*)nullptr, M, vrows, dgamma, dbeta, dcolsum)); \
+  } while (0)
+#define LN_BWDA_X(TX)                                                     \
+  do {                                                                    \
+    if (ddv == GOAT_F16) LN_BWDA(TX, __half);                             \
+    else if (ddv == GOAT_BF16) LN_BWDA(TX, __nv_bfloat16);                \
+    else LN_BWDA(TX, float);                                              \
+  } while (0)
+  if (x_dtype == GOAT_F32) LN_BWDA_X(float);
+  else if (x_dtype == GOAT_F16) LN_BWDA_X(__half);
+  else if (x_dtype == GOAT_BF16) LN_BWDA_X(__nv_bfloat16);
+  else GOAT_CHECK(false, "goat_layernorm_bwd_acc: bad x dtype");
+#undef LN_BWDA_X
+#undef LN_BWDA
   return GOAT_OK;
 }
 

@@ -132,9 +132,29 @@ def _vdst(param):
     return d
 
 
+def _adst(param):
+    """flat-gradient destination a kernel may ACCUMULATE into (the optimizer left the buffer zeroed), else None"""
+    if param is None:
+        return None
+    d = getattr(param, "_goat_grad", None)
+    if d is None or not d.is_contiguous():
+        return None
+    return d
+
+
 def _ln_bwd(dy32, x, gamma, mean, rstd, dres, cdt16, p, seed, seed_ptr, gamma_p, beta_p, bias_p=None):
     """LayerNorm backward with dgamma / dbeta (/ the producing Linear's bias grad) landing in the flat gradient
     buffer when there is one.  -> (dx32, dx16-or-None, dgamma, dbeta, dbias) with None for in-place grads."""
+    ag, ab, ac = _adst(gamma_p), _adst(beta_p), _adst(bias_p)
+    if x.shape[1] == 768 and ag is not None and ab is not None and (bias_p is None or ac is not None):
+        # one kernel: column sums added into the flat gradient views with atomics (no finalize launch)
+        dx32, dx16, _, _, _ = ops.layernorm_bwd(dy32, x, gamma, mean, rstd, dres, True, cdt16, p, seed, seed_ptr,
+                                                want_colsum=bias_p is not None, dgamma_out=ag, dbeta_out=ab,
+                                                dcol_out=ac, accumulate=True)
+        for q in (gamma_p, beta_p, bias_p):
+            if q is not None:
+                q._goat_fresh = False
+        return dx32, dx16, None, None, None
     og, ob = _vdst(gamma_p), _vdst(beta_p)
     oc = _vdst(bias_p)
     dx32, dx16, dg, db, dcol = ops.layernorm_bwd(dy32, x, gamma, mean, rstd, dres, True, cdt16, p, seed, seed_ptr,

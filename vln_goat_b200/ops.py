@@ -185,9 +185,11 @@ def layernorm_fwd(x, gamma, beta, eps, want32=True, dtype16=None):
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None, drop_p=0.0, drop_seed=0,
-                  seed_ptr=None, want_colsum=False, dgamma_out=None, dbeta_out=None, dcol_out=None):
+                  seed_ptr=None, want_colsum=False, dgamma_out=None, dbeta_out=None, dcol_out=None, accumulate=False):
     """-> (dx32 or None, dx16 or None, dgamma [H], dbeta [H], dcolsum [H] or None)
-    *_out: optional contiguous fp32 [H] destinations (e.g. flat gradient views) written instead of new tensors."""
+    *_out: optional contiguous fp32 [H] destinations (e.g. flat gradient views) written instead of new tensors.
+    accumulate=True (H == 768): dgamma / dbeta / dcolsum are ADDED to the destinations by the one kernel (fp32 atomics,
+    no finalize launch); destinations that are not given are fresh zeros."""
     _req_cuda(dy, x, gamma, mean, rstd, dres)
     M, H = x.shape
     if dy.dtype != torch.float32 or not dy.is_contiguous() or tuple(dy.shape) != (M, H):
@@ -198,10 +200,19 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want32=True, dtype16=None
     for o in (dgamma_out, dbeta_out, dcol_out):
         if o is not None and (o.dtype != torch.float32 or o.numel() != H or not o.is_contiguous()):
             raise ValueError("layernorm_bwd: *_out must be contiguous fp32 [H]")
-    dgamma = dgamma_out if dgamma_out is not None else torch.empty((H,), device=dev, dtype=torch.float32)
-    dbeta = dbeta_out if dbeta_out is not None else torch.empty((H,), device=dev, dtype=torch.float32)
-    dcol = (dcol_out if dcol_out is not None else torch.empty((H,), device=dev, dtype=torch.float32)) \
+    accumulate = accumulate and H == 768
+    new = torch.zeros if accumulate else torch.empty
+    dgamma = dgamma_out if dgamma_out is not None else new((H,), device=dev, dtype=torch.float32)
+    dbeta = dbeta_out if dbeta_out is not None else new((H,), device=dev, dtype=torch.float32)
+    dcol = (dcol_out if dcol_out is not None else new((H,), device=dev, dtype=torch.float32)) \
         if want_colsum else None
+    if accumulate:
+        rc = _lib.lib().goat_layernorm_bwd_acc(_p(dy), _p(x), dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32),
+                                               _p(dx16), dt(dtype16) if dtype16 is not None else F16, drop_p, drop_seed,
+                                               _p(seed_ptr), _p(dgamma), _p(dbeta), _p(dcol), M, H, _stream())
+        _lib.check(rc, "goat_layernorm_bwd_acc")
+        LAUNCHES[0] += 1
+        return dx32, dx16, dgamma, dbeta, dcol
     ws = torch.empty((_lib.lib().goat_layernorm_bwd_workspace_bytes(M, H),), device=dev, dtype=torch.uint8)
     rc = _lib.lib().goat_layernorm_bwd(_p(dy), _p(x), dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
                                        dt(dtype16) if dtype16 is not None else F16, drop_p, drop_seed, _p(seed_ptr),
