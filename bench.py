@@ -403,9 +403,21 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
             umma_flop += fl * cnt
             n_umma += cnt
     achieved = umma_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
+    # DRAM bytes moved by the same launches, from the committed ncu pass over one step (profiles/r01c_*)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("gemm_launches") == n_umma:
+            traffic = tj["gemm_dram_bytes_per_step"]
+            traffic_src = ("profiles/r01c_launches_one_step.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+                           "%d GEMM launches of one step (ncu, cold cache)" % n_umma)
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": "gemm_umma2_kernel / gemm_umma_kernel (tcgen05.mma cta_group::2 + TMA; all %d tensor-core GEMM launches of one step, "
                       "each shape re-timed as 20 graph-captured launches)" % n_umma,
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_unit": "bytes per step over the same launches", "traffic_source": traffic_src,
             "peak_source": which, "flop_per_step": umma_flop, "gemm_ms_per_step": umma_ms,
             "gemm_share_of_step": umma_ms / step_ms if step_ms else None,
             "step_tflops": umma_flop / (step_ms * 1e-3) / 1e12 if step_ms else None}
