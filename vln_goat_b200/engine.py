@@ -110,11 +110,8 @@ class FlatParams(object):
 
     def all_reduce(self, group=None):
         """Sum the flat gradient over ranks (the average is applied by the optimizer kernel's pre-scale)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=group)
-            return dist.get_world_size(group)
-        return 1
+        from .dist_utils import all_reduce_sum_
+        return all_reduce_sum_(self.g, group)
 
     def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, grad_scale=1.0,
                    correct_bias=True):
