@@ -120,5 +120,10 @@ if which in ("all", "misc"):
     y32, y16, mean, rstd = ops.layernorm_fwd(x32, g, bt, 1e-12, True, dt)
     timeit("ln fwd 5120x768", lambda: ops.layernorm_fwd(x32, g, bt, 1e-12, True, dt), bytes_=M * 768 * 10)
     timeit("ln bwd 5120x768", lambda: ops.layernorm_bwd(x32, x32, g, mean, rstd, None, True, dt, 0.1, 3, None, want_colsum=True), bytes_=M * 768 * 14)
+    gacc = torch.zeros(768, device=dev); bacc = torch.zeros(768, device=dev); cacc = torch.zeros(768, device=dev)
+    timeit("ln bwd acc 5120x768", lambda: ops.layernorm_bwd(x32, x32, g, mean, rstd, None, True, dt, 0.1, 3, None, want_colsum=True, dgamma_out=gacc, dbeta_out=bacc, dcol_out=cacc, accumulate=True), bytes_=M * 768 * 14)
     timeit("colsum 5120x2304", lambda: ops.colsum(dqkv), bytes_=M * 2304 * 2)
     timeit("colsum 5120x3072", lambda: ops.colsum(dz), bytes_=M * 3072 * 2)
+    c23 = torch.zeros(2304, device=dev); c30 = torch.zeros(3072, device=dev)
+    timeit("colsum acc 5120x2304", lambda: ops.colsum(dqkv, out=c23, accumulate=True), bytes_=M * 2304 * 2)
+    timeit("colsum acc 5120x3072", lambda: ops.colsum(dz, out=c30, accumulate=True), bytes_=M * 3072 * 2)

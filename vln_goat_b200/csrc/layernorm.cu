@@ -234,17 +234,18 @@ ln_fwd_vec_kernel(const void* __restrict__ x, const float* __restrict__ gamma, c
 // ACC = true : the CTA totals are added straight into dgamma / dbeta / dcolsum with vector fp32 atomics (destinations
 //              zero-initialised or holding earlier contributions, e.g. flat-gradient views) -- no second kernel.
 template <typename TX, typename TD, int NV, bool ACC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                   float* __restrict__ dx32, void* __restrict__ dx16, float drop_p, unsigned long long drop_seed_,
                   const unsigned long long* __restrict__ drop_seed_ptr, float* __restrict__ partial, int M,
                   int rows_per_cta, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   constexpr int H = NV * 128;
-  extern __shared__ float sacc[];  // [4 warps][3][H]
+  extern __shared__ float sacc[];  // [warps][3][H]
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;       // 4 (partials + finalize) or 8 (atomic accumulate) warps
   float4 ag[NV], ab[NV], ac[NV], gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -255,7 +256,7 @@ ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, cons
   const int r1 = min(M, r0 + rows_per_cta);
   const float keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const unsigned long long drop_seed = drop_p > 0.f ? eff_seed(drop_seed_, drop_seed_ptr) : 0ull;
-  for (int row = r0 + warp; row < r1; row += 4) {
+  for (int row = r0 + warp; row < r1; row += nw) {
     const float mu = mean[row], rs = rstd[row];
     float4 xh[NV], g[NV];
     float s1 = 0.f, s2 = 0.f;
@@ -317,8 +318,7 @@ ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, cons
   if constexpr (ACC) {
     for (int e = threadIdx.x * 4; e < 3 * H; e += blockDim.x * 4) {
       float4 t = *reinterpret_cast<const float4*>(&sacc[e]);
-#pragma unroll
-      for (int w = 1; w < 4; ++w) {
+      for (int w = 1; w < nw; ++w) {
         const float4 u = *reinterpret_cast<const float4*>(&sacc[w * 3 * H + e]);
         t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
       }
@@ -329,8 +329,7 @@ ln_bwd_vec_kernel(const float* __restrict__ dy, const void* __restrict__ x, cons
   } else {
     for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) {
       float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) t += sacc[w * 3 * H + e];
+      for (int w = 0; w < nw; ++w) t += sacc[w * 3 * H + e];
       partial[(size_t)blockIdx.x * 3 * H + e] = t;
     }
   }
@@ -423,6 +422,7 @@ colsum_atomic_kernel(const T* __restrict__ x, int M, int N, int ld, int rows_per
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
   if (c0 < N) {   // N % VEC == 0: a lane's VEC columns are all in range or all out
+#pragma unroll 4
     for (int r = r0 + warp; r < r1; r += 8) {
       const uint4 w = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + c0);
       if constexpr (sizeof(T) == 4) {
@@ -619,9 +619,11 @@ extern "C" int goat_layernorm_bwd_acc(const float* dy, const void* x, int x_dtyp
   }
   if (M <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int vparts = ln_bwd_vec_parts(M);
+  // 8 warps per CTA, 2 CTAs per SM: 16 warps of 16-byte loads in flight per SM, and only 296 CTAs' worth of atomics
+  int vparts = (M + 15) / 16;
+  if (vparts > 296) vparts = 296;
   const int vrows = (M + vparts - 1) / vparts;
-  constexpr int VSMEM = 4 * 3 * 768 * 4;
+  constexpr int VSMEM = 8 * 3 * 768 * 4;
   const int ddv = dx16 ? dx16_dtype : GOAT_F16;
 #define LN_BWDA(TX, TD)                                                                                               \
   do {                                                                                                                \
@@ -630,7 +632,7 @@ extern "C" int goat_layernorm_bwd_acc(const float* dy, const void* x, int x_dtyp
       GOAT_CUDA(cudaFuncSetAttribute(ln_bwd_vec_kernel<TX, TD, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VSMEM)); \
       cfga = true;                                                                                                    \
     }                                                                                                                 \
-    GOAT_CUDA(launch_pdl(ln_bwd_vec_kernel<TX, TD, 6, true>, dim3(vparts), dim3(128), (size_t)VSMEM, st, dy, x, gamma, mean, rstd, \
+    GOAT_CUDA(launch_pdl(ln_bwd_vec_kernel<TX, TD, 6, true>, dim3(vparts), dim3(256), (size_t)VSMEM, st, dy, x, gamma, mean, rstd, \
         dres, dx32, dx16, drop_p, (unsigned long long)drop_seed,                                                      \
         reinterpret_cast<const unsigned long long*>(drop_seed_ptr), (float*)nullptr, M, vrows, dgamma, dbeta, dcolsum)); \
   } while (0)
@@ -683,7 +685,7 @@ extern "C" int goat_colsum_acc(const void* x, int dtype, int M, int N, int ld, f
   if (M <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int gx = (N + 32 * vec - 1) / (32 * vec);
-  int gy = (2 * 148 + gx - 1) / gx;                 // about two CTAs per SM in total
+  int gy = (4 * 148 + gx - 1) / gx;                 // about four CTAs (32 warps) per SM in total
   const int max_gy = (M + 15) / 16;                 // at least 16 rows (2 per warp) per CTA
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
