@@ -166,6 +166,63 @@ def test_attention_block_shape_sweep(B, Nq, Nk, dtype):
         assert _rel(v.grad, Pr[k].grad) < 4 * TOL[dtype], k
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_kv_cache_rollout_matches_uncached(dtype):
+    """Rollout-level K|V projection cache: three navigation-like steps attend to the SAME instruction
+    embeddings; with the cache the text K|V projection of each cross layer is computed once and its backward runs once
+    on the fp32-summed gradient.  Outputs are bit-identical, gradients agree to accumulation-order noise; the golden
+    xenc_sprels fixture (reference-generated) still matches when its single step runs through the cached path."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    g = golden("xenc_sprels")
+    shapes = {}
+    for i in range(3):
+        shapes.update(O.cross_layer_shapes("crossattention.%d." % i))
+    params = O.seeded_params(shapes, seed=2)
+    gm_len, tx_len = g["gmap_lens"].cuda(), g["txt_lens"].cuda()
+    torch.manual_seed(11)
+    steps = [g["gmap"].float()] + [torch.randn_like(g["gmap"].float()) for _ in range(2)]
+
+    def run(cache):
+        enc = _load(M.CrossmodalEncoder(GoatConfig()), params)
+        tx = _cuda_leaf(g["txt"])
+        qs = [_cuda_leaf(q) for q in steps]
+        outs = []
+        with runtime.compute(dtype), M.kv_cache_scope(cache):
+            loss = 0.0
+            for q in qs:
+                out = enc(q, M.gen_seq_masks(gm_len, 12), tx, M.gen_seq_masks(tx_len, 40))
+                outs.append(out)
+                loss = loss + (out * g["w_out"].cuda()).sum()
+            loss.backward()
+        return outs, tx.grad, [q.grad for q in qs], _grads(enc)
+
+    o0, dtx0, dq0, gr0 = run(None)
+    cache = M.KVCache()
+    o1, dtx1, dq1, gr1 = run(cache)
+    assert (cache.misses, cache.hits) == (3, 6)
+    for a, b in zip(o0, o1):
+        assert torch.equal(a, b)
+    tol = DIG[dtype]
+    assert _rel(dtx1, dtx0) < tol
+    for a, b in zip(dq0, dq1):
+        assert _rel(b, a) < tol
+    assert set(gr0) == set(gr1)
+    for k in gr0:
+        if ".key.bias" in k:
+            continue                                   # mathematically zero: pure rounding noise in both runs
+        assert _rel(gr1[k], gr0[k]) < tol, k
+    # single step through the cached path against the reference-generated fixture
+    enc = _load(M.CrossmodalEncoder(GoatConfig()), params)
+    gm, tx, sp = _cuda_leaf(g["gmap"]), _cuda_leaf(g["txt"]), _cuda_leaf(g["sprels"])
+    with runtime.compute(dtype), M.kv_cache_scope(M.KVCache()):
+        out = enc(gm, M.gen_seq_masks(gm_len, 12), tx, M.gen_seq_masks(tx_len, 40), graph_sprels=sp)
+        (out * g["w_out"].cuda()).sum().backward()
+    assert _rel(out, g["out"]) < TOL[dtype]
+    assert _rel(tx.grad, g["dtxt"]) < TOL[dtype]
+    assert_digests({k: v for k, v in g.items() if "lang_" not in k}, _grads(enc), rtol=DIG[dtype], key_bias_atol=KB[dtype])
+
+
 def test_no_cpu_fallback():
     from vln_goat_b200 import modules as M
     from vln_goat_b200.config import GoatConfig

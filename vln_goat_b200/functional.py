@@ -182,12 +182,22 @@ class AttnBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x32, x16, kv32, kv16, kmask, bias, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, Wqkv_c, bqkv,
-                Wo_c, cfg):
+                Wo_c, cfg, kvp32=None, kvp16=None):
+        """kvp32 / kvp16: optional K|V projection of the keys/values already computed by KVProjFn (rollout-level
+        cache, modules.KVCache): the projection GEMM is skipped here and its gradient is handed back as the (fp32)
+        gradient of kvp32, so autograd sums it over every step that used the cached projection."""
         ctx.set_materialize_grads(False)   # no zero-filled gradient for the non-differentiable 16-bit copy
         H = x32.shape[1]
         cdt = cfg.cdt
         xc = _c(x32, x16, cdt)
-        if not cfg.cross:
+        ctx.cached_kv = cfg.cross and kvp32 is not None
+        if ctx.cached_kv:
+            kvc = None
+            q2 = ops.gemm(xc, Wqkv_c[:H], bias=bqkv[:H], out_dtype=cdt)            # [M,H]
+            kvp = kvp32 if cdt == torch.float32 else kvp16                          # [Mk,2H]
+            k2, v2 = kvp[:, :H], kvp[:, H:]
+            qkv = q2
+        elif not cfg.cross:
             qkv = ops.gemm(xc, Wqkv_c, bias=bqkv, out_dtype=cdt)                   # [M,3H]
             q2, k2, v2 = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
             kvc = None
@@ -243,7 +253,14 @@ class AttnBlockFn(torch.autograd.Function):
                              dq2.unflatten(0, (B, Nq)), dk2.unflatten(0, (B, Nk)), dv2.unflatten(0, (B, Nk)),
                              kmask, bias, 0.125, cfg.attn_p, cfg.seed, cfg.seed_ptr, want_dbias=want_dbias)
         dkv32 = None
-        if not cfg.cross:
+        dkvp32 = None
+        if ctx.cached_kv:
+            dWq, = _wgrad((Wq,), dqkv, xc)
+            dbq, = _bgrad((bq,), dqkv)
+            dWk = dWv = dbk = dbv = None
+            dx32 = ops.gemm(dqkv, Wqkv_c[:H], b_mn=True, res=dpre32, out_dtype=torch.float32)
+            dkvp32 = dkvp if cdt == torch.float32 else ops.cast(dkvp, torch.float32)   # summed over steps in fp32
+        elif not cfg.cross:
             dWq, dWk, dWv = _wgrad((Wq, Wk, Wv), dqkv, xc)                                   # [3H,H]
             dbq, dbk, dbv = _bgrad((bq, bk, bv), dqkv)
             dx32 = ops.gemm(dqkv, Wqkv_c, b_mn=True, res=dpre32, out_dtype=torch.float32)   # [M,H]
@@ -256,7 +273,43 @@ class AttnBlockFn(torch.autograd.Function):
             if ctx.needs_input_grad[2]:
                 dkv32 = ops.gemm(dkvp, Wqkv_c[H:], b_mn=True, out_dtype=torch.float32)      # [Mk,H]
         return (dx32, None, dkv32, None, None, dbias, dWq, dbq, dWk, dbk, dWv, dbv,
-                dWo, dbo, dgamma, dbeta, None, None, None, None)
+                dWo, dbo, dgamma, dbeta, None, None, None, None, dkvp32, None)
+
+
+class KVProjFn(torch.autograd.Function):
+    """[K | V] = kv W_kv^T + b_kv of one cross-attention, as its own autograd node: a rollout computes it ONCE per
+    layer for the instruction embeddings and every navigation step reuses it (the reference re-projects
+    the same text 15 x 2 x 3 times per rollout, M/r2r/agent.py:575-590 -> P/model/Bert_backbone.py:221-224).
+    Returns (kvp32 fp32 [Mk,2H], kvp16 16-bit copy or None).  The steps' gradients arrive summed (fp32) and the
+    projection's dgrad / wgrad GEMMs and bias sums run once."""
+
+    @staticmethod
+    def forward(ctx, kv32, kv16, Wk, bk, Wv, bv, Wkv_c, bkv, cdt):
+        ctx.set_materialize_grads(False)
+        kvc = _c(kv32, kv16, cdt)
+        kvp16 = None
+        if cdt == torch.float32:
+            kvp32 = ops.gemm(kvc, Wkv_c, bias=bkv, out_dtype=torch.float32)
+        else:
+            kvp16 = torch.empty((kvc.shape[0], Wkv_c.shape[0]), device=kvc.device, dtype=cdt)
+            kvp32 = ops.gemm(kvc, Wkv_c, bias=bkv, out_dtype=torch.float32, out2=kvp16)
+            ctx.mark_non_differentiable(kvp16)
+        ctx.cdt = cdt
+        ctx.params = (Wk, bk, Wv, bv)
+        ctx.save_for_backward(kvc, Wkv_c)
+        return kvp32, kvp16
+
+    @staticmethod
+    def backward(ctx, dkvp32, _d16):
+        if dkvp32 is None:
+            return (None,) * 9
+        kvc, Wkv_c = ctx.saved_tensors
+        Wk, bk, Wv, bv = ctx.params
+        dkvp_c = dkvp32.contiguous() if ctx.cdt == torch.float32 else ops.cast(dkvp32.contiguous(), ctx.cdt)
+        dWk, dWv = _wgrad((Wk, Wv), dkvp_c, kvc)
+        dbk, dbv = _bgrad((bk, bv), dkvp_c)
+        dkv32 = ops.gemm(dkvp_c, Wkv_c, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        return dkv32, None, dWk, dbk, dWv, dbv, None, None, None
 
 
 FFNCfg = namedtuple("FFNCfg", "eps hid_p seed seed_ptr cdt")

@@ -114,6 +114,59 @@ def _mask_parts(mask, B, Nq, Nk):
     return None, m.expand(B, Nq, Nk).contiguous()
 
 
+class KVCache(object):
+    """Rollout-level cache of cross-attention K|V projections.  While a cache is active
+    (``kv_cache_scope``) a cross-attention whose key/value tensor is the one it saw last time -- same storage, shape and
+    version counter: the instruction embeddings a navigation rollout passes to every step, or the FACL prototypes --
+    reuses its projection instead of recomputing it; gradients of all uses are summed by autograd and the projection's
+    backward runs once.  An entry keeps its source tensor alive, so a pointer match cannot be a recycled allocation.
+    ``clear()`` at the start of a rollout (GlocalTextPathNavCMT does it in ``language`` mode)."""
+
+    def __init__(self):
+        self.entries = {}
+        self.hits = 0
+        self.misses = 0
+
+    def clear(self):
+        self.entries.clear()
+
+    def get(self, attn, enc, cdt):
+        s = attn.self
+        tag = (enc.x32.data_ptr(), tuple(enc.x32.shape), enc.x32._version, cdt, torch.is_grad_enabled(),
+               s.key.weight._version, s.value.weight._version, s.key.weight.data_ptr())
+        e = self.entries.get(id(attn))
+        if e is not None and e[0] == tag:
+            self.hits += 1
+            return e[2], e[3]
+        self.misses += 1
+        H = s.all_head_size
+        wkv = runtime.wc_cat((s.query.weight, s.key.weight, s.value.weight), cdt)[H:]
+        bkv = runtime.wc_cat((s.query.bias, s.key.bias, s.value.bias), torch.float32)[H:]
+        kvp32, kvp16 = Fn.KVProjFn.apply(enc.x32, enc.x16, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
+                                         wkv, bkv, cdt)
+        self.entries[id(attn)] = (tag, enc.x32, kvp32, kvp16)
+        return kvp32, kvp16
+
+
+_ACTIVE_KV_CACHE = [None]
+
+
+class kv_cache_scope(object):
+    """``with kv_cache_scope(cache):`` -- cross-attentions run inside reuse / fill ``cache`` (None switches it off)."""
+
+    def __init__(self, cache):
+        self.cache = cache
+
+    def __enter__(self):
+        self.prev = _ACTIVE_KV_CACHE[0]
+        _ACTIVE_KV_CACHE[0] = self.cache
+        return self.cache
+
+    def __exit__(self, *exc):
+        _ACTIVE_KV_CACHE[0] = self.prev
+        return False
+
+
 def _p_drop(module_training, p):
     return float(p) if (module_training and p > 0.0) else 0.0
 
@@ -182,12 +235,16 @@ class BertAttention(nn.Module):
                          _p_drop(self.training, s.dropout.p), _p_drop(self.training, o.dropout.p), seed,
                          Fn.seed_ptr(), cross, cdt)
         qkv = (s.query.weight, s.key.weight, s.value.weight)
+        kvp32 = kvp16 = None
+        cache = _ACTIVE_KV_CACHE[0] if cross else None
+        if cache is not None:
+            kvp32, kvp16 = cache.get(self, enc, cdt)
         y32, y16 = Fn.AttnBlockFn.apply(
             x.x32, x.x16, enc.x32 if cross else None, enc.x16 if cross else None, kmask, bias,
             s.query.weight, s.query.bias, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
             o.dense.weight, o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias,
             runtime.wc_cat(qkv, cdt), runtime.wc_cat((s.query.bias, s.key.bias, s.value.bias), torch.float32),
-            runtime.wc(o.dense.weight, cdt), cfg)
+            runtime.wc(o.dense.weight, cdt), cfg, kvp32, kvp16)
         return Act(y32, y16, x.B, x.N)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,

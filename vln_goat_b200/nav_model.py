@@ -63,6 +63,8 @@ class GlocalTextPathNavCMT(nn.Module):
         if config.do_front_txt:
             self.front_txt_encoder = G.FrontDoorEncoder(config)      # constructed, never called (reference :607-608)
         self.apply(_init_bert_weights(config))
+        # rollout-level K|V projection cache of the cross-attentions; config.kv_cache=False turns it off
+        self._kv_cache = M.KVCache() if getattr(config, "kv_cache", True) else None
         if getattr(config, "fix_lang_embedding", False) or getattr(config, "fix_local_branch", False):
             for mod in (self.embeddings, self.lang_encoder):
                 for p in mod.parameters():
@@ -94,6 +96,15 @@ class GlocalTextPathNavCMT(nn.Module):
                                     gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
                                     vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats=None, front_gmap_feats=None,
                                     flops_count=False):
+        with M.kv_cache_scope(self._kv_cache):
+            return self._navigation_step(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
+                                         gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
+                                         vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats,
+                                         front_gmap_feats, flops_count)
+
+    def _navigation_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
+                         gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
+                         vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats, front_gmap_feats, flops_count):
         ge, le = self.global_encoder, self.local_encoder
         # global branch
         gmap_embeds = gmap_img_embeds + ge.step_embed(gmap_step_ids) + G._pos_embed(ge.gmap_pos_embeddings, gmap_pos_fts)
@@ -133,6 +144,8 @@ class GlocalTextPathNavCMT(nn.Module):
 
     def forward(self, mode, batch, **kwargs):
         if mode == "language":
+            if self._kv_cache is not None:
+                self._kv_cache.clear()      # a new rollout: new instruction embeddings
             return self.forward_text(batch["txt_ids"], batch["txt_masks"], batch["instr_z_direction_features"],
                                      batch["instr_z_direction_pzs"], batch["instr_z_landmark_features"],
                                      batch["instr_z_landmark_pzs"], batch["front_txt_feats"])
