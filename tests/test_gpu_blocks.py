@@ -223,6 +223,83 @@ def test_kv_cache_rollout_matches_uncached(dtype):
     assert_digests({k: v for k, v in g.items() if "lang_" not in k}, _grads(enc), rtol=DIG[dtype], key_bias_atol=KB[dtype])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_c2_full_size_batch_matches_oracle_on_a_slice(dtype):
+    """BASELINE.json configs[1] at FULL size (batch 64, 80 tokens, [stop]+36 views, 6 + 3 layers) on the GPU.  Samples
+    are independent on this path, so samples {0, 1, 63} of the batch-64 outputs and the gradient of a loss that only
+    touches those samples must equal the CPU oracle run on just those three samples (seconds on CPU)."""
+    from vln_goat_b200 import runtime, workloads
+    from vln_goat_b200.config import GoatConfig
+    B, L, Nq, H = 64, 80, 37, 768
+    gen = torch.Generator().manual_seed(5)
+    txt = torch.randn(B, L, H, generator=gen)
+    vp = torch.randn(B, Nq, H, generator=gen)
+    vp[:, 0] = 0.0
+    lens = torch.randint(L // 2, L + 1, (B,), generator=gen)
+    lens[0] = L
+    tm = O.gen_seq_masks(lens, L)
+    vm = torch.ones(B, Nq, dtype=torch.bool)
+    pick = torch.tensor([0, 1, 63])
+    params = O.seeded_params(O.c2_shapes(), seed=0)
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    t_ref, v_ref = O.c2_forward(P, txt[pick], tm[pick], vp[pick], vm[pick])
+    O.c2_loss(t_ref, v_ref).backward()
+    model = workloads.C2CrossEncoder(GoatConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    model.load_state_dict(params, strict=False)
+    model = model.cuda().train()
+    with runtime.compute(dtype):
+        t, v = model(txt.cuda(), tm.cuda(), vp.cuda(), vm.cuda())
+        loss = 0.5 * (t[pick.cuda()] ** 2).mean() + 0.5 * (v[pick.cuda()] ** 2).mean()
+        loss.backward()
+    tol = TOL[dtype] * (2 if dtype == torch.float32 else 1)      # 9 layers deep
+    assert _rel(t[pick.cuda()], t_ref.detach()) < tol
+    assert _rel(v[pick.cuda()], v_ref.detach()) < tol
+    assert abs(loss.item() - O.c2_loss(t_ref, v_ref).item()) < 1e-4 * (1 if dtype == torch.float32 else 50)
+    got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    for k in ("lang_encoder.layer.0.attention.self.query.weight", "lang_encoder.layer.5.output.dense.weight",
+              "local_encoder.encoder.crossattention.2.output.dense.weight",
+              "local_encoder.encoder.crossattention.0.crossattention.self.value.weight",
+              "local_encoder.encoder.crossattention.1.intermediate.dense.bias"):
+        ref = P[k].grad
+        err = (got[k].cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+        assert err < (1e-3 if dtype == torch.float32 else 5e-2), (k, err)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_c5_long_instruction_cross_layer(dtype):
+    """BASELINE.json configs[4] shape per GPU: RxR-length text (512 tokens, ragged) x [stop]+36 views, batch 4 -- one
+    BertCrossLayer forward + backward against the CPU oracle (keys beyond 128 run the chunked tcgen05 attention)."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    B, Nq, Nk, H = 4, 37, 512, 768
+    gen = torch.Generator().manual_seed(8)
+    q0 = torch.randn(B, Nq, H, generator=gen)
+    kv0 = torch.randn(B, Nk, H, generator=gen)
+    w = torch.randn(B, Nq, H, generator=gen)
+    lens = torch.tensor([512, 300, 129, 477])
+    params = O.seeded_params(O.cross_layer_shapes(), seed=4)
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    q64, kv64 = q0.clone().requires_grad_(True), kv0.clone().requires_grad_(True)
+    qm_ref = O.extend_neg_masks(torch.ones(B, Nq, dtype=torch.bool))
+    km_ref = O.extend_neg_masks(O.gen_seq_masks(lens, Nk))
+    ref = O.cross_layer(P, "", q64, kv64, qm_ref, km_ref)
+    (ref * w).sum().backward()
+    layer = _load(M.BertCrossLayer(GoatConfig()), params)
+    q, kv = _cuda_leaf(q0), _cuda_leaf(kv0)
+    with runtime.compute(dtype):
+        out = layer(q, kv, attention_mask=qm_ref.cuda(), encoder_attention_mask=km_ref.cuda())[0]
+        (out * w.cuda()).sum().backward()
+    assert _rel(out, ref.detach()) < TOL[dtype]
+    assert _rel(q.grad, q64.grad) < TOL[dtype] * 2
+    assert _rel(kv.grad, kv64.grad) < TOL[dtype] * 2
+    got = _grads(layer)
+    for k in ("crossattention.self.value.weight", "output.dense.weight", "attention.self.query.weight"):
+        refg = P[k].grad
+        err = (got[k].cpu() - refg).abs().max().item() / max(refg.abs().max().item(), 1e-12)
+        assert err < DIG[dtype] * 2, (k, err)
+
+
 def test_no_cpu_fallback():
     from vln_goat_b200 import modules as M
     from vln_goat_b200.config import GoatConfig
