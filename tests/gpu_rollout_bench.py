@@ -49,6 +49,8 @@ def main():
     for t in range(T):
         _, pano, nav = synth.nav_inputs(B=B, L=L, seed=100 + t, G=G)
         nav["txt_masks"] = lang["txt_masks"]
+        if steps:       # the agent passes the SAME front-door prototypes at every step of a rollout (M/r2r/agent.py:567-583)
+            nav["front_vp_feats"], nav["front_gmap_feats"] = steps[0][1]["front_vp_feats"], steps[0][1]["front_gmap_feats"]
         steps.append((synth.batch_to(pano, dev), synth.batch_to(nav, dev)))
         targets.append(torch.zeros(B, dtype=torch.int64, device=dev))      # [stop] is always a valid action
     res = {}
@@ -79,4 +81,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if os.environ.get("PROFILE"):
+        import cProfile, pstats
+        cProfile.run("main()", "/tmp/rollout.prof")
+        pstats.Stats("/tmp/rollout.prof").sort_stats("tottime").print_stats(35)
+    else:
+        main()

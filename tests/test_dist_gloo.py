@@ -55,7 +55,7 @@ def _worker(rank, world, port, ret):
         assert w == world
         flat *= 1.0 / w                       # the optimizer kernel's grad_scale
         if rank == 0:
-            ret.put(flat.clone())
+            ret.put(flat.numpy().copy())     # by value: a torch tensor would travel as a shared-memory handle that dies with the worker
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -88,7 +88,7 @@ def test_two_rank_gradient_average_equals_global_batch_gradient():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
-    got = ret.get(timeout=240)
+    got = torch.from_numpy(ret.get(timeout=240))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

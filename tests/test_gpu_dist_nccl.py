@@ -43,7 +43,7 @@ def _batch(seed, dev, B=4, L=80, Nq=37, H=768):
     return tuple(t.to(dev) for t in (txt, tm, vp, vm))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, shard):
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -54,31 +54,52 @@ def _worker(rank, world, port, ret):
         b = _batch(100 + rank, dev)
         active = engine.active_parameters(model, loss_fn, b)
         flat = engine.FlatParams(model, shadow_dtype=torch.bfloat16, only=active)
-        ts = engine.TrainStep(flat, loss_fn, b, use_graph=False, lr=1e-3, max_grad_norm=-1.0)
+        ts = engine.TrainStep(flat, loss_fn, b, use_graph=False, lr=1e-3, max_grad_norm=0.05, shard_optimizer=shard)
         ts.step(b)
+        ts.step(b)
+        flat.sync_master()          # sharded steps leave the fp32 master weights current on their owner rank only
         torch.cuda.synchronize()
-        ret.put((rank, flat.p.detach().cpu()))
+        ret.put((rank, flat.p[:flat.numel].detach().cpu().numpy(), flat.shadow[:flat.numel].float().cpu().numpy(),
+                 flat.grad_norm.item()))     # numpy: pickled by value (tensors travel as handles that die with the worker)
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_step_matches_averaged_gradient_step():
+@pytest.mark.parametrize("shard", [False, True])
+def test_two_rank_step_matches_averaged_gradient_step(shard):
+    """shard=False: all-reduce + full AdamW on every rank; shard=True: reduce-scatter + AdamW on 1/world + all-gather."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, shard)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(ret.get(timeout=400) for _ in range(2))
+    import queue
+    res = []
+    for _ in range(120):                      # poll: a worker that died must fail the test, not hang it
+        try:
+            res.append(ret.get(timeout=2))
+        except queue.Empty:
+            pass
+        if len(res) == 2:
+            break
+        assert all(p.is_alive() or p.exitcode == 0 for p in procs), "a worker exited with %s" % [p.exitcode for p in procs]
+    assert len(res) == 2, "workers timed out"
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
-    assert torch.equal(got[0], got[1])          # identical replicas after the all-reduced step
+    got = {r[0]: torch.from_numpy(r[1]) for r in res}
+    shadows = {r[0]: torch.from_numpy(r[2]) for r in res}
+    norms = {r[0]: r[3] for r in res}
+    assert torch.equal(got[0], got[1])          # identical replicas after the data-parallel steps
+    assert torch.equal(shadows[0], shadows[1])
+    assert torch.equal(shadows[0], got[0].bfloat16().float())      # the operand shadow is the rounded master copy
+    assert abs(norms[0] - norms[1]) < 1e-6 * max(1.0, norms[0])
     # 1-rank reference: accumulate both batches' gradients, scale by 1/2
     dev = torch.device("cuda", 0)
     engine, model, loss_fn = _setup(dev)
@@ -86,12 +107,14 @@ def test_two_rank_step_matches_averaged_gradient_step():
     active = engine.active_parameters(model, loss_fn, b0)
     flat = engine.FlatParams(model, shadow_dtype=torch.bfloat16, only=active)
     flat.g.zero_()
-    for b in (b0, b1):
-        flat.begin_step()
-        loss_fn(*b).backward()
-    flat.adamw_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_grad_norm=-1.0, grad_scale=0.5)
+    for _ in range(2):              # two optimizer steps, each on the average of the two ranks' gradients
+        for b in (b0, b1):
+            flat.begin_step()
+            loss_fn(*b).backward()
+        flat.adamw_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_grad_norm=0.05, grad_scale=0.5)
     torch.cuda.synchronize()
-    ref = flat.p.detach().cpu()
+    ref = flat.p[:flat.numel].detach().cpu()
+    assert abs(flat.grad_norm.item() - norms[0]) < 1e-3 * max(1.0, norms[0])
     # AdamW's first step moves every weight by ~lr * sign(g): compare the updates, tolerance for atomic-order noise
     err = (got[0] - ref).abs().max().item()
     assert err < 2e-4, err

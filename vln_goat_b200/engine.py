@@ -36,10 +36,12 @@ class FlatParams(object):
     (and, in the other group, their biases) back to back.
     """
 
-    def __init__(self, model, shadow_dtype=None, no_decay=NO_DECAY, only=None):
+    def __init__(self, model, shadow_dtype=None, no_decay=NO_DECAY, only=None, group=None):
         """``only``: optional collection of parameters to flatten (see ``active_parameters``); the rest of the
         model is left untouched and never updated -- the reference's AdamW likewise skips parameters whose
-        ``grad`` is None (P/optim/adamw.py:66-67), which DDP's find_unused_parameters=True relies on."""
+        ``grad`` is None (P/optim/adamw.py:66-67), which DDP's find_unused_parameters=True relies on.
+        ``group``: the data-parallel process group (default: the world); the buffers are padded so that they split
+        into equal 16-byte aligned shards, one per rank (``sharded_step``)."""
         named = []
         seen = set()
         keep = None if only is None else set(id(p) for p in only)
@@ -65,13 +67,21 @@ class FlatParams(object):
                 self.n_decay = off
         if not decay:
             self.n_decay = 0
+        from .dist_utils import world_size
+        self.group = group
+        self.world = world_size(group)
         self.numel = off
-        self.p = torch.zeros(off, device=dev, dtype=torch.float32)
-        self.g = torch.zeros(off, device=dev, dtype=torch.float32)
-        self.m = torch.zeros(off, device=dev, dtype=torch.float32)
-        self.v = torch.zeros(off, device=dev, dtype=torch.float32)
+        unit = 8 * self.world
+        self.padded = (off + unit - 1) // unit * unit        # equal shards of a multiple of 8 elements per rank
+        tot = self.padded
+        self.p = torch.zeros(tot, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(tot, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(tot, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(tot, device=dev, dtype=torch.float32)
         self.shadow_dtype = shadow_dtype if shadow_dtype in (torch.float16, torch.bfloat16) else None
-        self.shadow = torch.zeros(off, device=dev, dtype=self.shadow_dtype) if self.shadow_dtype else None
+        self.shadow = torch.zeros(tot, device=dev, dtype=self.shadow_dtype) if self.shadow_dtype else None
+        self._g_shard = self._x_shard = None
+        self.master_synced = True
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             self.p[o:o + n].copy_(p.detach().reshape(-1))
@@ -113,10 +123,13 @@ class FlatParams(object):
         from .dist_utils import all_reduce_sum_
         return all_reduce_sum_(self.g, group)
 
-    def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, grad_scale=1.0,
-                   correct_bias=True):
-        """clip_grad_norm_(max_grad_norm) + AdamW (P/optim/adamw.py:85-110 numerics) on the flat buffer; the gradient
-        buffer is cleared in the same pass (weight-gradient GEMMs accumulate into it, see functional._wgrad)."""
+    # ------------------------------------------------------------------------------------------
+    # sharded optimizer step (world > 1): reduce-scatter -> clip + AdamW on this rank's 1/world of the buffer ->
+    # all-gather of what the next forward reads.  Same arithmetic as all_reduce() + adamw_step(grad_scale=1/world)
+    # -- every element is updated by exactly one rank from the same summed gradient and the same global norm -- at
+    # 3/4 of the all-reduce's bytes (fp32 reduce-scatter + 16-bit all-gather) and 1/world of the optimizer's HBM pass.
+    # ------------------------------------------------------------------------------------------
+    def _hp_upload(self, lr, betas, eps, weight_decay, max_grad_norm, grad_scale, correct_bias):
         self.step_count += 1
         t = self.step_count
         # pageable source on purpose: the runtime stages a small pageable H2D copy before returning, so the
@@ -125,6 +138,71 @@ class FlatParams(object):
                           (1.0 - betas[0] ** t) if correct_bias else 1.0,
                           (1.0 - betas[1] ** t) if correct_bias else 1.0, max_grad_norm, grad_scale], dtype=torch.float32)
         self._hp.copy_(h, non_blocking=True)
+
+    def sharded_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, correct_bias=True):
+        """One data-parallel optimizer step with the optimizer state's work split over the ranks (see above).
+        Afterwards every rank holds the new 16-bit operand shadow and the new fp32 no-decay vectors (biases,
+        LayerNorm); the fp32 master WEIGHTS are current only on their owner rank until ``sync_master()``
+        (call it before ``state_dict()`` / checkpointing).  Without a 16-bit shadow (fp32 compute) the whole fp32
+        buffer is all-gathered every step instead."""
+        import torch.distributed as dist
+        W = self.world
+        if W <= 1:
+            return self.adamw_step(lr, betas, eps, weight_decay, max_grad_norm, 1.0, correct_bias)
+        rank = dist.get_rank(self.group)
+        S = self.padded // W
+        lo = rank * S
+        if self._g_shard is None:
+            self._g_shard = torch.zeros(S, device=self.p.device, dtype=torch.float32)
+            self._x_shard = torch.zeros(S, device=self.p.device, dtype=self.shadow_dtype or torch.float32)
+        dist.reduce_scatter_tensor(self._g_shard, self.g, op=dist.ReduceOp.SUM, group=self.group)
+        self.g.zero_()                      # the next step's gradients accumulate into a cleared buffer
+        self._hp_upload(lr, betas, eps, weight_decay, max_grad_norm, 1.0 / W, correct_bias)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nparts = C.c_int(0)
+        L = _lib.lib()
+        _lib.check(L.goat_sumsq(self._g_shard.data_ptr(), S, self._partial.data_ptr(), C.byref(nparts), st), "goat_sumsq")
+        tot = self._partial[:nparts.value].sum().reshape(1)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)     # global squared norm of the summed gradient
+        self._partial[:1].copy_(tot)
+        sd = ops.dt(self.shadow_dtype) if self.shadow is not None else 0
+        n_decay_local = min(max(self.n_decay - lo, 0), S)
+        _lib.check(L.goat_adamw_step(self.p[lo:lo + S].data_ptr(), self._g_shard.data_ptr(), self.m[lo:lo + S].data_ptr(),
+                                     self.v[lo:lo + S].data_ptr(),
+                                     self.shadow[lo:lo + S].data_ptr() if self.shadow is not None else None, sd, S,
+                                     n_decay_local, self._hp.data_ptr(), self._partial.data_ptr(), 1,
+                                     self.grad_norm.data_ptr(), 0, st), "goat_adamw_step")
+        ops.LAUNCHES[0] += 2
+        if self.shadow is not None:
+            self._x_shard.copy_(self.shadow[lo:lo + S])
+            dist.all_gather_into_tensor(self.shadow, self._x_shard, group=self.group)
+            # fp32 vectors the kernels read directly (biases, LayerNorm): broadcast each owner's piece of the no-decay tail
+            for r in range(W):
+                a, b = max(self.n_decay, r * S), min(self.numel, (r + 1) * S)
+                if a < b:
+                    dist.broadcast(self.p[a:b], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                                   group=self.group)
+            self.master_synced = False
+        else:
+            self._x_shard.copy_(self.p[lo:lo + S])
+            dist.all_gather_into_tensor(self.p, self._x_shard, group=self.group)
+
+    def sync_master(self):
+        """All-gather the fp32 master weights after sharded steps (every rank then holds the full, identical fp32
+        parameters: call before state_dict() / checkpointing)."""
+        import torch.distributed as dist
+        if self.world > 1 and not self.master_synced:
+            S = self.padded // self.world
+            lo = dist.get_rank(self.group) * S
+            tmp = self.p[lo:lo + S].clone()
+            dist.all_gather_into_tensor(self.p, tmp, group=self.group)
+            self.master_synced = True
+
+    def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, grad_scale=1.0,
+                   correct_bias=True):
+        """clip_grad_norm_(max_grad_norm) + AdamW (P/optim/adamw.py:85-110 numerics) on the flat buffer; the gradient
+        buffer is cleared in the same pass (weight-gradient GEMMs accumulate into it, see functional._wgrad)."""
+        self._hp_upload(lr, betas, eps, weight_decay, max_grad_norm, grad_scale, correct_bias)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         nparts = C.c_int(0)
         L = _lib.lib()
@@ -167,8 +245,11 @@ class TrainStep(object):
     """
 
     def __init__(self, flat, loss_fn, example_inputs, lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01,
-                 max_grad_norm=5.0, use_graph=True, warmup_iters=2):
+                 max_grad_norm=5.0, use_graph=True, warmup_iters=2, shard_optimizer=True):
+        """``shard_optimizer``: at world size > 1 use FlatParams.sharded_step (reduce-scatter, 1/world of the AdamW
+        pass per rank, all-gather of the operand shadow) instead of all-reduce + a full AdamW pass on every rank."""
         self.flat, self.loss_fn = flat, loss_fn
+        self.shard_optimizer = shard_optimizer
         self.opt = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         self.static_inputs = [t.clone() if t.is_cuda else t.cuda() for t in example_inputs]
         dev = self.static_inputs[0].device
@@ -216,8 +297,11 @@ class TrainStep(object):
             self.graph.replay()
         else:
             self._fwd_bwd()
-        world = self.flat.all_reduce()
-        self.flat.adamw_step(grad_scale=1.0 / world, **self.opt)
+        if self.shard_optimizer and self.flat.world > 1:
+            self.flat.sharded_step(**self.opt)
+        else:
+            world = self.flat.all_reduce(self.flat.group)
+            self.flat.adamw_step(grad_scale=1.0 / world, **self.opt)
         return self.loss
 
 

@@ -26,7 +26,13 @@ def dt(t):
         raise TypeError("unsupported dtype %s" % (t if isinstance(t, torch.dtype) else t.dtype))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """torch's current stream as a raw handle (torch.cuda.current_stream() costs ~15 us of Python per call)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
