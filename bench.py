@@ -303,6 +303,7 @@ def run_goat(args):
 
     if rank == 0:
         roof = gemm_roofline(torch, ops, ts, cdt, ms / args.steps)
+        roof_attn = attention_roofline(torch, ops, cdt, ms / args.steps)
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -319,6 +320,7 @@ def run_goat(args):
             "gpu_launches": ts.launches_per_step * args.steps,
             "gpu_launches_per_step": ts.launches_per_step,
             "roofline": roof,
+            "roofline_attention": roof_attn,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = time_cpu(2, 1, 16)
@@ -403,14 +405,14 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
             umma_flop += fl * cnt
             n_umma += cnt
     achieved = umma_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
-    # DRAM bytes moved by the same launches, from the committed ncu pass over one step (profiles/r01c_*)
+    # DRAM bytes moved by the same launches, from the committed ncu pass over one step (profiles/r01d_*)
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("gemm_launches") == n_umma:
             traffic = tj["gemm_dram_bytes_per_step"]
-            traffic_src = ("profiles/r01c_launches_one_step.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+            traffic_src = ("profiles/r01d_launches_one_step.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
                            "%d GEMM launches of one step (ncu, cold cache)" % n_umma)
     except Exception:
         pass
@@ -421,6 +423,66 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
             "peak_source": which, "flop_per_step": umma_flop, "gemm_ms_per_step": umma_ms,
             "gemm_share_of_step": umma_ms / step_ms if step_ms else None,
             "step_tflops": umma_flop / (step_ms * 1e-3) / 1e12 if step_ms else None}
+
+
+def attention_roofline(torch, ops, cdt, step_ms):
+    """The other regime of SURVEY.md 8d: the attention core (QK^T, softmax, PV and its backward) is HBM / latency
+    bound.  Algorithmic bytes of the step's 24 attention launches / their device time (20 graph-captured launches each)."""
+    if cdt == torch.float32:
+        return None
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs")
+    which = "MEASURED_PEAKS.json hbm_gbs"
+    if peak is None:
+        peak, which = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    dev = torch.device("cuda", torch.cuda.current_device())
+    heads, p_drop = 12, 0.1
+
+    def graph_ms(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    tot_ms, tot_bytes, n = 0.0, 0.0, 0
+    # (count per step, Nq, Nk): 6 text self-attentions, 3 view self-attentions, 3 view -> text cross-attentions
+    for cnt, Nq, Nk in ((6, L, L), (3, NQ, NQ), (3, NQ, L)):
+        q = torch.randn(B, Nq, H, device=dev).to(cdt)
+        k = torch.randn(B, Nk, H, device=dev).to(cdt)
+        v = torch.randn(B, Nk, H, device=dev).to(cdt)
+        km = torch.zeros(B, Nk, device=dev)
+        w = torch.randn(B, Nq, H, device=dev).to(cdt)
+        o, lse = ops.attn_fwd(q, k, v, heads, km, drop_p=p_drop, drop_seed=3)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        f_ms = graph_ms(lambda: ops.attn_fwd(q, k, v, heads, km, drop_p=p_drop, drop_seed=3))
+        b_ms = graph_ms(lambda: ops.attn_bwd(w, q, k, v, o, lse, heads, dq, dk, dv, km, drop_p=p_drop, drop_seed=3))
+        f_bytes = 2.0 * B * H * (2 * Nq + 2 * Nk) + 4.0 * B * Nk          # q, o + k, v (16-bit) + key mask
+        b_bytes = 2.0 * B * H * (4 * Nq + 4 * Nk) + 4.0 * B * Nk          # q, o, dO, dQ + k, v, dK, dV
+        tot_ms += cnt * (f_ms + b_ms)
+        tot_bytes += cnt * (f_bytes + b_bytes)
+        n += 2 * cnt
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "attn_fwd_pipe_kernel + attn_bwd_pipe_kernel (all %d attention launches of one step, "
+                                      "dropout 0.1, each shape re-timed as 20 graph-captured launches)" % n,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": which, "bytes_per_step": tot_bytes, "attention_ms_per_step": tot_ms,
+            "attention_share_of_step": tot_ms / step_ms if step_ms else None}
 
 
 def main():
