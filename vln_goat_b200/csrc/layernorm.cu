@@ -1,5 +1,7 @@
 // LayerNorm forward / backward (fp32 statistics), column sums and dtype casts.
 // Memory-bound helpers: one warp per row, 16-byte vector accesses, two-stage deterministic column reductions.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace goat {
@@ -619,9 +621,12 @@ extern "C" int goat_layernorm_bwd_acc(const float* dy, const void* x, int x_dtyp
   }
   if (M <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // 8 warps per CTA, 2 CTAs per SM: 16 warps of 16-byte loads in flight per SM, and only 296 CTAs' worth of atomics
+  // 8 warps per CTA, ONE CTA per SM: measured at 5120 x 768 (B200): 74 CTAs 17.2 us, 148 CTAs 10.9 us (5.0 TB/s),
+  // 222 CTAs 14.2 us, 296 CTAs 13.5 us, 444 CTAs 15.4 us -- past one CTA per SM the same-address atomics of the column
+  // sums cost more than the extra loads in flight buy.  GOAT_LN_PARTS overrides (tuning).
+  static const int max_parts = [] { const char* e = getenv("GOAT_LN_PARTS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
   int vparts = (M + 15) / 16;
-  if (vparts > 296) vparts = 296;
+  if (vparts > max_parts) vparts = max_parts;
   const int vrows = (M + vparts - 1) / vparts;
   constexpr int VSMEM = 8 * 3 * 768 * 4;
   const int ddv = dx16 ? dx16_dtype : GOAT_F16;
