@@ -63,8 +63,10 @@ int goat_device_supported(void);
  * dtype F16/BF16 -> tcgen05.mma (TMA-fed, TMEM accumulators) when K, lda, ldb are multiples of 8
  * and K >= 16; otherwise, and always for F32, the SIMT kernel.  force_simt=1 selects the SIMT
  * kernel (used by tests as an on-device cross-check).
- * The tcgen05 kernel is persistent (one CTA per SM walking 128x128 tiles) with two TMEM accumulators so the
- * epilogue of one tile overlaps the main loop of the next.
+ * M > 128 runs the CTA-pair kernel (gemm_umma2.cu): a cluster of two CTAs shares one 256 x 256 (or 256 x 128) tile
+ * through tcgen05.mma.cta_group::2, each CTA staging its 128 rows of A and half of B; M <= 128 runs the single-CTA
+ * 128 x 128 kernel.  Both are persistent with two TMEM accumulators (the epilogue of one tile overlaps the main loop of
+ * the next) and are launched with programmatic dependent launch (GOAT_PDL=0 disables it).
  * ------------------------------------------------------------------------------------------ */
 typedef struct goat_gemm_args {
   int M, N, K;
