@@ -276,12 +276,30 @@ def gen_nav_full():
          w_pf=w_pf, target=target, loss=loss.detach(), **grads_digest(model))
 
 
+def gen_nav_rollout():
+    """3-step teacher-forced rollout through the UNMODIFIED reference model (BACL + FACL on), one backward."""
+    ref_shim.install("nav")
+    import models.vilmodel_GOAT as V
+    cfg = ref_shim.nav_config()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    model = load_seeded(V.GlocalTextPathNavCMT(cfg).eval(), seed=23)
+    lang, per_step, targets = synth.rollout_inputs()
+    loss, logits, clss, txt = synth.run_rollout(model, lang, per_step, targets)
+    loss.backward()
+    arrs = {"loss": loss.detach(), "txt_embeds": txt}
+    for t, (lg, c) in enumerate(zip(logits, clss)):
+        arrs["fused_logits_%d" % t] = lg
+        arrs["cls_embeds_%d" % t] = c
+    save("nav_rollout", **arrs, **grads_digest(model))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tree", choices=["pretrain", "nav", "pretrain_full", "nav_full", "all"], default="all")
+    ap.add_argument("--tree", choices=["pretrain", "nav", "pretrain_full", "nav_full", "nav_rollout", "all"], default="all")
     a = ap.parse_args()
     if a.tree == "all":
-        for t in ("pretrain", "nav", "pretrain_full", "nav_full"):
+        for t in ("pretrain", "nav", "pretrain_full", "nav_full", "nav_rollout"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "--tree", t])
     elif a.tree == "pretrain":
         gen_pretrain()
@@ -289,5 +307,7 @@ if __name__ == "__main__":
         gen_pretrain_full()
     elif a.tree == "nav_full":
         gen_nav_full()
+    elif a.tree == "nav_rollout":
+        gen_nav_rollout()
     else:
         gen_nav()

@@ -211,3 +211,42 @@ def nav_inputs(B=3, L=20, seed=0, views=36, G=9):
            "front_gmap_feats": torch.tanh(torch.randn(B, 24, H, generator=g)),
            "mem_embeds": torch.randn(B, H, generator=g) * 0.5}
     return lang, pano, nav
+
+
+def rollout_inputs(steps=3, B=3, L=20, seed=40):
+    """Synthetic 3-step fine-tune rollout (shared by tests/golden/make_golden.py and tests/test_gpu_models.py): one instruction,
+    per-step panorama / navigation inputs, the FACL prototypes constant over the rollout as in M/r2r/agent.py:567-583."""
+    lang, _, nav0 = nav_inputs(B=B, L=L, seed=seed)
+    per_step = []
+    for t in range(steps):
+        _, pano, nav = nav_inputs(B=B, L=L, seed=seed + 1 + t)
+        nav["txt_masks"] = lang["txt_masks"]
+        nav["front_vp_feats"], nav["front_gmap_feats"] = nav0["front_vp_feats"], nav0["front_gmap_feats"]
+        per_step.append((pano, nav))
+    targets = [torch.tensor([4, 0, 5]), torch.tensor([0, 4, 0]), torch.tensor([5, 4, 6])][:steps]   # [stop] or unvisited nodes
+    return lang, per_step, targets
+
+
+def run_rollout(model, lang, per_step, targets, to_dev=lambda d: d):
+    """language once, then panorama + navigation per step; the [MEM] token of step t+1 is step t's cls_embeds (agent.py:592);
+    teacher-forced cross-entropy summed over the steps.  -> (loss, [fused_logits], [cls_embeds], txt_embeds)"""
+    from collections import defaultdict
+    dd = lambda d: defaultdict(lambda: None, to_dev(d))
+    txt = model("language", dd(lang))
+    loss, logits, clss, mem = 0.0, [], [], None
+    for (pano, nav), tgt in zip(per_step, targets):
+        pe, pm, pf = model("panorama", dd(pano))
+        navb = dict(to_dev(nav))
+        m0 = navb.pop("mem_embeds")
+        mem_t = m0 if mem is None else mem
+        navb["txt_embeds"] = txt
+        navb["vp_img_embeds"] = torch.cat([torch.zeros_like(pe[:, :1]), mem_t.unsqueeze(1), pe], 1)
+        gi = navb["gmap_img_embeds"].clone()
+        gi = torch.cat([gi[:, :1], mem_t.unsqueeze(1), gi[:, 2:]], 1)          # gmap row 1 = [MEM] as well (agent.py:175)
+        navb["gmap_img_embeds"] = gi
+        outs = model("navigation", defaultdict(lambda: None, navb))
+        mem = outs["cls_embeds"]
+        logits.append(outs["fused_logits"])
+        clss.append(outs["cls_embeds"])
+        loss = loss + torch.nn.functional.cross_entropy(outs["fused_logits"], tgt.to(outs["fused_logits"].device), reduction="sum")
+    return loss, logits, clss, txt

@@ -285,6 +285,44 @@ def test_nav_full_language_panorama_navigation(dtype):
                    key_bias_atol=None if dtype == torch.float32 else 64.0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kv_cache", [True, False])
+def test_nav_rollout_three_steps_vs_reference(dtype, kv_cache):
+    """a teacher-forced rollout (language once, then panorama + navigation for three steps,
+    the [MEM] token chaining cls_embeds from step to step, cross-entropy summed, ONE backward) against the fixture the
+    UNMODIFIED reference produced for the same inputs (tests/golden/make_golden.py --tree nav_rollout).  With the
+    rollout-level K|V cache on (the default) the six instruction projections and the two FACL prototype projections are
+    computed at step 0 and reused at steps 1 and 2."""
+    from vln_goat_b200 import nav_model, runtime
+    gold = golden("nav_rollout")
+    cfg = _nav_cfg()
+    cfg.kv_cache = kv_cache
+    model = _seed_model(nav_model.GlocalTextPathNavCMT(cfg), 23).cuda().eval()
+    lang, per_step, targets = synth.rollout_inputs()
+    # device copies made once; the FACL prototypes are the SAME tensors at every step, as in the agent
+    fv, fg = per_step[0][1]["front_vp_feats"].cuda(), per_step[0][1]["front_gmap_feats"].cuda()
+    dev_steps = []
+    for pano, nav in per_step:
+        n = synth.batch_to(nav, "cuda")
+        n["front_vp_feats"], n["front_gmap_feats"] = fv, fg
+        dev_steps.append((synth.batch_to(pano, "cuda"), n))
+    tol, dig = FULL_TOL[dtype], FULL_DIG[dtype]
+    with runtime.compute(dtype):
+        loss, logits, clss, txt = synth.run_rollout(model, synth.batch_to(lang, "cuda"), dev_steps, targets)
+        loss.backward()
+    assert _rel(txt, gold["txt_embeds"]) < tol
+    for t in range(3):
+        assert _rel(logits[t], gold["fused_logits_%d" % t]) < tol * (1 + t), t      # errors chain through [MEM]
+        assert _rel(clss[t], gold["cls_embeds_%d" % t]) < tol * (1 + t), t
+    assert abs(loss.item() - gold["loss"].item()) < tol * max(1.0, abs(gold["loss"].item())) * 10
+    assert_digests(gold, _grads(model), rtol=dig, atol=1e-3 if dtype == torch.float32 else 1e-1,
+                   key_bias_atol=None if dtype == torch.float32 else 64.0)
+    if kv_cache:
+        assert (model._kv_cache.misses, model._kv_cache.hits) == (8, 16)
+    else:
+        assert model._kv_cache is None
+
+
 def test_vlnbert_wrapper_feature_dropout_and_modes():
     """VLNBert(mode, batch): panorama applies the environment feature dropout unless already_dropout (model.py:28-32)."""
     from types import SimpleNamespace
