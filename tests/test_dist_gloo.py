@@ -94,3 +94,102 @@ def test_two_rank_gradient_average_equals_global_batch_gradient():
         assert p.exitcode == 0
     err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
     assert err < 1e-5, err
+
+
+# ----------------------------------------------------------------------------------------------
+# sharded optimizer step: layout arithmetic + the data flow of engine.FlatParams.sharded_step, emulated on CPU
+# ----------------------------------------------------------------------------------------------
+def test_shard_layout_and_tail_pieces():
+    from vln_goat_b200 import dist_utils as D
+    for world in (1, 2, 4, 8):
+        numel = 1000 * world + 123
+        padded = (numel + 8 * world - 1) // (8 * world) * (8 * world)
+        n_decay = 700 * world + 16
+        covered, decayed = 0, 0
+        for r in range(world):
+            S, lo, ndl = D.shard_layout(padded, n_decay, world, r)
+            assert S % 8 == 0 and lo == r * S and 0 <= ndl <= S
+            covered += S
+            decayed += ndl
+        assert covered == padded and decayed == n_decay        # every element owned once, decay region preserved
+        pieces = D.tail_pieces(n_decay, numel, padded // world, world)
+        assert pieces[0][1] == n_decay and pieces[-1][2] == numel
+        assert all(a[2] == b[1] for a, b in zip(pieces, pieces[1:]))
+        assert all(r * (padded // world) <= a and b <= (r + 1) * (padded // world) for r, a, b in pieces)
+    with pytest.raises(ValueError):
+        D.shard_layout(100, 10, 3, 0)
+
+
+def _sharded_worker(rank, world, port, ret):
+    """engine.FlatParams.sharded_step with torch CPU arithmetic in place of the two kernels (oracle AdamW = the numerics
+    goat_adamw_step implements): reduce-scatter, global norm from shard sums, AdamW on the shard, all-gather, tail."""
+    import torch.distributed as dist
+    from oracle import goat_oracle as O
+    from vln_goat_b200 import dist_utils as D
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        numel, n_decay, padded, p0, grads = _sharded_problem(world)
+        p = torch.zeros(padded); p[:numel] = p0
+        m, v = torch.zeros(padded), torch.zeros(padded)
+        S, lo, ndl = D.shard_layout(padded, n_decay, world, rank)
+        for step in (1, 2):
+            g = torch.zeros(padded); g[:numel] = grads[rank] * step          # this rank's local gradient
+            gs = torch.empty(S)
+            D.reduce_scatter_sum(gs, g)
+            tot = (gs.double() ** 2).sum().float().reshape(1)
+            dist.all_reduce(tot)
+            pre = 1.0 / world
+            norm = tot.sqrt() * pre
+            coef = pre * min(1.0, (MAXN / (norm + 1e-6)).item())
+            sl = slice(lo, lo + S)
+            gg = gs * coef
+            if ndl > 0:
+                O.adamw_step(p[lo:lo + ndl], gg[:ndl], m[lo:lo + ndl], v[lo:lo + ndl], step, LR, BETAS, 1e-6, WD)
+            if ndl < S:
+                O.adamw_step(p[lo + ndl:lo + S], gg[ndl:], m[lo + ndl:lo + S], v[lo + ndl:lo + S], step, LR, BETAS, 1e-6, 0.0)
+            D.all_gather_flat(p, p[sl].clone())        # (the product gathers the 16-bit shadow + the fp32 tail; same layout)
+        if rank == 0:
+            ret.put(p[:numel].numpy().copy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+LR, BETAS, WD, MAXN = 1e-2, (0.9, 0.98), 0.01, 0.5
+
+
+def _sharded_problem(world):
+    g = torch.Generator().manual_seed(17)
+    numel, n_decay = 1000 + 37, 800
+    padded = (numel + 8 * world - 1) // (8 * world) * (8 * world)
+    p0 = torch.randn(numel, generator=g)
+    grads = [torch.randn(numel, generator=g) for _ in range(world)]
+    return numel, n_decay, padded, p0, grads
+
+
+@pytest.mark.timeout(300)
+def test_sharded_step_data_flow_matches_unsharded_reference():
+    import torch.multiprocessing as mp
+    from oracle import goat_oracle as O
+    world = 2
+    numel, n_decay, padded, p0, grads = _sharded_problem(world)
+    # 1-process reference: average the ranks' gradients, clip by the global norm, AdamW with decay on [0, n_decay)
+    p, m, v = p0.clone(), torch.zeros(numel), torch.zeros(numel)
+    for step in (1, 2):
+        g = sum(gr * step for gr in grads) / world
+        _, coef = O.clip_grad_norm([g], MAXN)
+        g = g * coef
+        O.adamw_step(p[:n_decay], g[:n_decay], m[:n_decay], v[:n_decay], step, LR, BETAS, 1e-6, WD)
+        O.adamw_step(p[n_decay:], g[n_decay:], m[n_decay:], v[n_decay:], step, LR, BETAS, 1e-6, 0.0)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, ret)) for r in range(world)]
+    for q in procs:
+        q.start()
+    got = torch.from_numpy(ret.get(timeout=240))
+    for q in procs:
+        q.join(timeout=60)
+        assert q.exitcode == 0
+    assert (got - p).abs().max().item() < 1e-6

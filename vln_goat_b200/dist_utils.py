@@ -48,3 +48,65 @@ def flatten_grads(params):
     sizes = [p.numel() for p in params]
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
     return flat, sizes
+
+
+# --------------------------------------------------------------------------------------
+# sharded optimizer step (engine.FlatParams.sharded_step): layout arithmetic + collectives that also run on gloo
+# --------------------------------------------------------------------------------------
+def shard_layout(padded, n_decay, world, rank):
+    """The flat buffer of ``padded`` elements (a multiple of 8 * world) is cut into ``world`` equal shards; rank r owns
+    [r*S, (r+1)*S).  -> (S, lo, n_decay_local): shard size, first element, and how many of the shard's leading elements
+    lie in the weight-decayed region [0, n_decay) of the whole buffer."""
+    if padded % (8 * world):
+        raise ValueError("padded size %d is not a multiple of 8 * world (%d)" % (padded, 8 * world))
+    S = padded // world
+    lo = rank * S
+    return S, lo, min(max(n_decay - lo, 0), S)
+
+
+def tail_pieces(n_decay, numel, S, world):
+    """The no-decay tail [n_decay, numel) (fp32 vectors every rank reads directly: biases, LayerNorm) split by owning
+    shard -> [(owner rank, a, b)] with a < b."""
+    out = []
+    for r in range(world):
+        a, b = max(n_decay, r * S), min(numel, (r + 1) * S)
+        if a < b:
+            out.append((r, a, b))
+    return out
+
+
+def _backend(group=None):
+    import torch.distributed as dist
+    return dist.get_backend(group)
+
+
+def reduce_scatter_sum(out, inp, group=None):
+    """out[S] = this rank's shard of the element-wise SUM of inp[world*S] over the ranks.  NCCL: one reduce-scatter;
+    other backends (gloo in the CPU tests has none): all-reduce a copy and keep the local slice."""
+    import torch.distributed as dist
+    if _backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+        return
+    tmp = inp.clone()
+    dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+    S = out.numel()
+    r = dist.get_rank(group)
+    out.copy_(tmp[r * S:(r + 1) * S])
+
+
+def all_gather_flat(out, shard, group=None):
+    """out[world*S] = concatenation of every rank's shard[S] in rank order."""
+    import torch.distributed as dist
+    if _backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, shard, group=group)
+        return
+    W = dist.get_world_size(group)
+    parts = [torch.empty_like(shard) for _ in range(W)]
+    dist.all_gather(parts, shard, group=group)
+    out.copy_(torch.cat(parts))
+
+
+def group_src(r, group=None):
+    """global rank of group rank r (what dist.broadcast's ``src`` expects)"""
+    import torch.distributed as dist
+    return dist.get_global_rank(group, r) if group is not None else r

@@ -149,13 +149,13 @@ class FlatParams(object):
         W = self.world
         if W <= 1:
             return self.adamw_step(lr, betas, eps, weight_decay, max_grad_norm, 1.0, correct_bias)
+        from . import dist_utils as D
         rank = dist.get_rank(self.group)
-        S = self.padded // W
-        lo = rank * S
+        S, lo, n_decay_local = D.shard_layout(self.padded, self.n_decay, W, rank)
         if self._g_shard is None:
             self._g_shard = torch.zeros(S, device=self.p.device, dtype=torch.float32)
             self._x_shard = torch.zeros(S, device=self.p.device, dtype=self.shadow_dtype or torch.float32)
-        dist.reduce_scatter_tensor(self._g_shard, self.g, op=dist.ReduceOp.SUM, group=self.group)
+        D.reduce_scatter_sum(self._g_shard, self.g, self.group)
         self.g.zero_()                      # the next step's gradients accumulate into a cleared buffer
         self._hp_upload(lr, betas, eps, weight_decay, max_grad_norm, 1.0 / W, correct_bias)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -166,7 +166,6 @@ class FlatParams(object):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)     # global squared norm of the summed gradient
         self._partial[:1].copy_(tot)
         sd = ops.dt(self.shadow_dtype) if self.shadow is not None else 0
-        n_decay_local = min(max(self.n_decay - lo, 0), S)
         _lib.check(L.goat_adamw_step(self.p[lo:lo + S].data_ptr(), self._g_shard.data_ptr(), self.m[lo:lo + S].data_ptr(),
                                      self.v[lo:lo + S].data_ptr(),
                                      self.shadow[lo:lo + S].data_ptr() if self.shadow is not None else None, sd, S,
@@ -175,27 +174,23 @@ class FlatParams(object):
         ops.LAUNCHES[0] += 2
         if self.shadow is not None:
             self._x_shard.copy_(self.shadow[lo:lo + S])
-            dist.all_gather_into_tensor(self.shadow, self._x_shard, group=self.group)
+            D.all_gather_flat(self.shadow, self._x_shard, self.group)
             # fp32 vectors the kernels read directly (biases, LayerNorm): broadcast each owner's piece of the no-decay tail
-            for r in range(W):
-                a, b = max(self.n_decay, r * S), min(self.numel, (r + 1) * S)
-                if a < b:
-                    dist.broadcast(self.p[a:b], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
-                                   group=self.group)
+            for r, a, b in D.tail_pieces(self.n_decay, self.numel, S, W):
+                dist.broadcast(self.p[a:b], src=D.group_src(r, self.group), group=self.group)
             self.master_synced = False
         else:
             self._x_shard.copy_(self.p[lo:lo + S])
-            dist.all_gather_into_tensor(self.p, self._x_shard, group=self.group)
+            D.all_gather_flat(self.p, self._x_shard, self.group)
 
     def sync_master(self):
         """All-gather the fp32 master weights after sharded steps (every rank then holds the full, identical fp32
         parameters: call before state_dict() / checkpointing)."""
         import torch.distributed as dist
         if self.world > 1 and not self.master_synced:
-            S = self.padded // self.world
-            lo = dist.get_rank(self.group) * S
-            tmp = self.p[lo:lo + S].clone()
-            dist.all_gather_into_tensor(self.p, tmp, group=self.group)
+            from . import dist_utils as D
+            S, lo, _ = D.shard_layout(self.padded, self.n_decay, self.world, dist.get_rank(self.group))
+            D.all_gather_flat(self.p, self.p[lo:lo + S].clone(), self.group)
             self.master_synced = True
 
     def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, grad_scale=1.0,
