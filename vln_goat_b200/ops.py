@@ -169,7 +169,8 @@ def attn_bwd(do, q, k, v, o, lse, heads, dq, dk, dv, kmask=None, bias=None, scal
         dbias = torch.zeros((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
         a.dbias = dbias.data_ptr()
     _lib.check(_lib.lib().goat_attn_core_bwd(C.byref(a), _stream()), "goat_attn_core_bwd")
-    LAUNCHES[0] += 2
+    # one kernel on the tcgen05 paths (16-bit, Nq <= 128), two (dQ, then dK/dV) on the fp32-math SIMT path
+    LAUNCHES[0] += 1 if (q.dtype != torch.float32 and q.shape[1] <= 128 and not force_simt) else 2
     return dbias
 
 
