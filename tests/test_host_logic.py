@@ -154,3 +154,54 @@ def test_fusion_index_reproduces_reference_loops():
     idx = G.build_fusion_index(nav["gmap_vpids"], nav["gmap_visited_masks"], nav["vp_cand_vpids"], 38, 2, 2)
     assert torch.allclose(_apply_fusion_index(gl, ll, idx), ref, atol=1e-6)
     assert (ref != gl).any()
+
+
+def _remap_pretrain_to_finetune(ckpt):
+    """The key remap of M/models/vlnbert_init.py:52-69 restated, followed by what HF's from_pretrained does when the
+    target class IS the base model (base_model_prefix 'bert'): a leading 'bert.' is stripped."""
+    out = {}
+    for k, v in ckpt.items():
+        if k.startswith("module"):
+            k = k[7:]
+        if k.startswith("vln_bert"):
+            k = "bert" + k[8:]
+        if "_head" in k or "sap_fuse" in k:
+            out["bert." + k] = v
+        elif "tim" in k or "temperature" in k:
+            out[("bert." + k) if "self_encoder" not in k else k] = v
+        else:
+            out[k] = v
+    return {(k[5:] if k.startswith("bert.") else k): v for k, v in out.items()}
+
+
+def test_pretrain_checkpoint_remaps_into_the_finetune_model():
+    """a checkpoint saved from the pretrain model (ModelSaver strips 'module.',
+    P/utils/save.py:47-63) goes through the reference's own key remap and loads into the fine-tune model: every shared
+    block is covered with identical shapes; only pretrain-only heads are left over, only fine-tune-only modules missing."""
+    from vln_goat_b200 import nav_model, pretrain_model
+    from vln_goat_b200.config import GoatConfig
+    pre = pretrain_model.GlocalTextPathCMTPreTraining(GoatConfig())
+    ckpt = {("module." + k): v for k, v in pre.state_dict().items()}            # as saved under DDP
+    remapped = _remap_pretrain_to_finetune(ckpt)
+    nav = nav_model.GlocalTextPathNavCMT(_nav_cfg())
+    target = nav.state_dict()
+    shared = [k for k in remapped if k in target]
+    assert all(tuple(remapped[k].shape) == tuple(target[k].shape) for k in shared)
+    res = nav.load_state_dict({k: remapped[k] for k in shared}, strict=False)
+    assert not res.unexpected_keys
+    # the whole cross-modal core arrives from the pretrain checkpoint
+    for fam in ("embeddings.", "lang_encoder.layer.", "img_embeddings.img_linear", "img_embeddings.img_self_encoder.",
+                "local_encoder.encoder.crossattention.", "global_encoder.encoder.crossattention.",
+                "global_encoder.gmap_pos_embeddings.", "local_encoder.vp_pos_embeddings.", "global_sap_head.",
+                "local_sap_head.", "sap_fuse_linear."):
+        fam_keys = [k for k in target if k.startswith(fam)]
+        assert fam_keys and all(k in remapped for k in fam_keys if "lang_" not in k[len(fam):]), fam
+    # left over: pretrain-only heads / pretrain-only sub-blocks of BertCrossLayer (P/model/Bert_backbone.py:673-676)
+    leftover = [k for k in remapped if k not in target]
+    assert leftover and all(any(t in k for t in ("mlm_head", "lang_self_attn", "lang_inter", "lang_output", "tim_",
+                                                  "img_self_attn")) for k in leftover), leftover[:5]
+    # missing: modules that only exist in the fine-tune model (BACL dictionaries / projections, FACL encoders, poolers,
+    # the per-step history token)
+    missing = set(res.missing_keys)
+    assert missing and all(any(t in k for t in ("z_", "do_img", "front_", "pooler", "local_his", "instr_", "concat_linear",
+                                                 "img_after_linear")) for k in missing), sorted(missing)[:8]
