@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- R2R pretrain steps/sec on the GOAT cross-modal hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl goat|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl goat|reference] [--dtype fp16|bf16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (config.workload = "C2"): BASELINE.json configs[1], "full 9-layer GOAT cross-encoder fwd+bwd,
-batch=64": LanguageEncoder (6 RobertaLayers, 80 tokens) + CrossmodalEncoder (3 BertCrossLayers, [stop]+36 view
-tokens x 80 text tokens), hidden 768, dropout 0.1 as shipped, random-init weights, synthetic N(0,1) features.
-One step = forward + backward + (N>1) NCCL gradient all-reduce + global-norm clip + AdamW, i.e. what
-P/train_r2r_goat.py:301-366 does per batch.  Weak scaling: every rank runs its own batch of 64.
+Workload (config.workload = "C3-step"): ONE optimizer step of the full pretraining model -- what the reference's loop
+does per batch (P/train_r2r_goat.py:301-366): ``GlocalTextPathCMTPreTraining(batch, task, compute_loss=True)`` (208 M
+parameters: RoBERTa embeddings, 6-layer language encoder, panorama embeddings + 2-layer pano encoder + adaptive fusion,
+global-map and local 3-layer cross-modal encoders, MLM / SAP / CFP heads), ``loss.mean().backward()``, (N>1) gradient
+exchange, global-norm clip, AdamW.  Tasks alternate MLM, SAP, CFP (round-robin over steps); batch = 64 samples per
+GPU (weak scaling), 36 views x 768, 80 tokens, trajectories of 1-5 panoramas, dropout 0.1 as shipped, random-init
+weights, synthetic features with the collate layout of P/data/tasks.py.
 
 One JSON line on rank 0:
-  value     device-resident steps/s (inputs already in HBM), N ranks x K steps / max-over-ranks CUDA-event time
-  e2e       the same step driven from pinned HOST buffers: per step H2D of the batch + D2H of the loss
-  roofline  the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of the step's GEMM launches / their
-            CUDA-event time, re-timed live launch by launch after the timed region, vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU restatement of the reference path (oracle/, torch fp32, all host cores) on the same step
---impl reference times only that CPU path (the reference is pure PyTorch; /root/reference does not travel to the
-GPU box, so the committed oracle port, pinned to the reference by tests/golden, stands in for it).
+  value       device-resident steps/s (prepared batches already in HBM): N ranks x K steps / max-over-ranks CUDA-event time
+  e2e         the same steps driven from HOST batch dicts: per step the host index builders + padding
+              (batching.prepare_pretrain), H2D of the step's inputs from pinned memory, the step, D2H of the loss
+  parity_max_err  max error of the benchmarked model / dtype / batch size against the CPU oracle (logits, CFP embeddings,
+              MLM scores, losses), relative to max(1, max|ref|) -- the north-star tolerance is 1e-3 (16-bit) / 1e-5 (fp32)
+  roofline    the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of the GEMM launches of one MLM+SAP+CFP round /
+              their CUDA-event time, re-timed live launch by launch, vs MEASURED_PEAKS.json (burst: timed alone)
+  roofline_attention  the attention core launches of the same round vs the HBM copy roofline
+  sustained   the same device-resident loop run for >= 2 s (clocks settle well below the burst the K steps see)
+  cpu_baseline        the CPU restatement of the same step (oracle/, torch fp32, all host cores), one step per task
+  eager_b200_baseline the same restatement run eagerly on the B200 (fp32 and autocast fp16): the honest denominator
+  c2          second line: BASELINE.json configs[1] (9-layer cross-encoder slice, batch 64) on the same kernels
+--impl reference times only the CPU path (the reference is pure PyTorch; /root/reference does not travel to the GPU
+box, so the committed oracle port, pinned to the reference by tests/golden, stands in for it).
 """
 import argparse
 import json
@@ -33,106 +42,129 @@ sys.path.insert(0, ROOT)
 
 METRIC = "R2R pretrain steps/sec (batch=64, 36 views×768, 80 tok) at 1/2/4/8 B200"
 B, L, NQ, H = 64, 80, 37, 768
+TASKS = ("mlm", "sap", "cfp")
+N_BATCHES = 4            # distinct host batches per task and rank, cycled
 OPT = dict(lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_grad_norm=5.0)  # P/config/r2r_GOAT_pretrain.json
+WORKLOAD = ("C3-step: full GlocalTextPathCMTPreTraining (208 M params) fwd+bwd+clip+AdamW, tasks MLM/SAP/CFP round-robin, "
+            "batch 64 per GPU, 36 views x 768, 80 tokens, 1-5 panoramas per trajectory")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=180)
+    ap.add_argument("--warmup", type=int, default=9)
     ap.add_argument("--impl", default="goat", choices=["goat", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity / rooflines / baselines / C2 (profiling runs)")
+    ap.add_argument("--selfcheck", action="store_true",
+                    help="N>1: assert bit-identical parameters and forward outputs across ranks after sharded steps")
     return ap.parse_args()
 
 
-# ------------------------------------------------------------------------------------------------
-# synthetic batch (same recipe on CPU and GPU arms)
-# ------------------------------------------------------------------------------------------------
-def make_batches(n, batch, seed):
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    out = []
-    for _ in range(n):
-        txt = torch.randn(batch, L, H, generator=g)
-        vp = torch.randn(batch, NQ, H, generator=g)
-        vp[:, 0] = 0.0  # the [stop] token is a zero embedding, P/model/vilmodel_goat.py:379-388
-        lens = torch.randint(L // 2, L + 1, (batch,), generator=g)
-        lens[0] = L
-        tm = torch.arange(L)[None, :] < lens[:, None]
-        vm = torch.ones(batch, NQ, dtype=torch.bool)
-        out.append((txt, tm, vp, vm))
-    return out
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: oracle restatement of the reference path (checker code used here only as the timed baseline)
+# CPU arm: oracle restatement of the reference step (checker code used here only as the timed baseline)
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(batch, seed=0):
+def oracle_params(device="cpu"):
+    """seeded parameters of the full pretraining model under the reference's state_dict names"""
     import torch
     from oracle import goat_oracle as O
-    torch.manual_seed(seed)
-    P = {k: v.clone().requires_grad_(True) for k, v in O.seeded_params(O.c2_shapes(), seed=0).items()}
-    M_ = {k: torch.zeros_like(v) for k, v in P.items()}
-    V_ = {k: torch.zeros_like(v) for k, v in P.items()}
+    from vln_goat_b200 import pretrain_model
+    from vln_goat_b200.config import GoatConfig
+    with torch.device("meta"):
+        m = pretrain_model.GlocalTextPathCMTPreTraining(GoatConfig(pretrain_tasks=TASKS))
+    shapes = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    P = O.seeded_params(shapes, seed=0)
+    P["bert.embeddings.word_embeddings.weight"] = P["mlm_head.predictions.decoder.weight"]   # tied
+    return {k: v.to(device) for k, v in P.items()}
+
+
+def oracle_step_fn(device="cpu", autocast=False):
+    """-> step(batch, task): forward + backward + clip + per-tensor AdamW of the oracle model (what the reference loop
+    does with its own modules, P/train_r2r_goat.py:301-366 + P/optim/adamw.py)."""
+    import torch
+    from oracle import goat_oracle as O
+    from oracle import goat_pretrain_oracle as PO
+    P = {k: v.clone().requires_grad_(True) for k, v in oracle_params(device).items() if "decoder.weight" not in k}
+    P["mlm_head.predictions.decoder.weight"] = P["bert.embeddings.word_embeddings.weight"]
+    leaves = {k: v for k, v in P.items() if "decoder.weight" not in k}
+    M_ = {k: torch.zeros_like(v) for k, v in leaves.items()}
+    V_ = {k: torch.zeros_like(v) for k, v in leaves.items()}
     state = {"t": 0}
     nodecay = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+    scaler = torch.amp.GradScaler("cuda") if autocast else None
 
-    def step(txt, tm, vp, vm):
-        for v in P.values():
+    def step(batch, task):
+        for v in leaves.values():
             v.grad = None
-        t, o = O.c2_forward(P, txt, tm, vp, vm)
-        loss = O.c2_loss(t, o)
-        loss.backward()
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.float16):
+                loss = PO.scalar_loss(P, batch, task)
+            scaler.scale(loss).backward()
+            inv = 1.0 / scaler.get_scale()
+        else:
+            loss = PO.scalar_loss(P, batch, task)
+            loss.backward()
+            inv = 1.0
         state["t"] += 1
         with torch.no_grad():
-            _, coef = O.clip_grad_norm([v.grad for v in P.values()], OPT["max_grad_norm"])
-            for k, v in P.items():
+            used = {k: v for k, v in leaves.items() if v.grad is not None}
+            _, coef = O.clip_grad_norm([v.grad * inv for v in used.values()], OPT["max_grad_norm"])
+            for k, v in used.items():
                 wd = 0.0 if any(nd in k for nd in nodecay) else OPT["weight_decay"]
-                O.adamw_step(v, v.grad * coef, M_[k], V_[k], state["t"], OPT["lr"], OPT["betas"], OPT["eps"], wd)
-        return float(loss)
+                O.adamw_step(v, v.grad * (inv * coef), M_[k], V_[k], state["t"], OPT["lr"], OPT["betas"], OPT["eps"], wd)
+        return float(loss.detach())
     return step
 
 
-def time_cpu(steps, warmup, sample_batch):
+def time_cpu(steps, warmup, budget_s=240.0):
+    """K timed steps (round-robin tasks) of the oracle step at the full batch 64 on all host cores."""
     import torch
+    from vln_goat_b200 import workloads
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(sample_batch)
-    batches = make_batches(2, sample_batch, seed=123)
+    step = oracle_step_fn("cpu")
+    batches = [workloads.synthetic_pretrain_batch(B, L, seed=123 + i) for i in range(2)]
+    t_w = time.perf_counter()
     for i in range(warmup):
-        step(*batches[i % 2])
+        step(batches[i % 2], TASKS[i % 3])
+    est = (time.perf_counter() - t_w) / max(warmup, 1)
+    if warmup and est * steps > budget_s:
+        steps = max(3, int(budget_s / est) // 3 * 3)
     t0 = time.perf_counter()
     for i in range(steps):
-        step(*batches[i % 2])
+        step(batches[i % 2], TASKS[i % 3])
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    # one batch-64 step costs 64/sample_batch sample steps (every op is linear in the batch; the optimizer part
-    # is batch independent and therefore over-counted in the reference's favour when sample_batch < 64)
-    value = (sample_batch / float(B)) / dt
-    return value, dt, cores
+    return 1.0 / dt, dt, cores, steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
-    value, dt, cores = time_cpu(steps, warm, sample)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    value, dt, cores, steps = time_cpu(steps, warm)
     n = max(1, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": n, "steps": steps,
-        "warmup": warm, "ms_per_step": dt * 1e3 * (B / sample), "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 6 RobertaLayer + 3 BertCrossLayer fwd+bwd+clip+AdamW, hidden 768, 80 tok x 37 view tokens",
-                   "global_batch": B, "per_gpu_batch": B, "device": "host CPU (the reference path is pure PyTorch)"},
+        "config": {"workload": WORKLOAD, "global_batch": B, "per_gpu_batch": B,
+                   "device": "host CPU (the reference path is pure PyTorch)"},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d timed steps on a %d-sample slice of the batch-64 step, scaled by %d/64; oracle/ "
-                                   "restatement of the reference modules (pinned by tests/golden), torch fp32, %d threads"
-                                   % (steps, sample, sample, cores)},
+                         "sample": "%d timed optimizer steps (tasks MLM/SAP/CFP round-robin) at the FULL batch 64; oracle/ "
+                                   "restatement of the reference model (pinned by tests/golden), torch fp32, %d threads"
+                                   % (steps, cores)},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,9 +213,8 @@ class Clocks(object):
                         reasons.add(nm)
             except Exception:
                 continue
-        # "under load": samples above 60 % of the max draw seen
         if pw:
-            thr = 0.6 * max(pw)
+            thr = 0.6 * max(pw)        # "under load": samples above 60 % of the max draw seen
             sm_l = [s for s, p in zip(sm, pw) if p >= thr] or sm
         else:
             sm_l = sm
@@ -195,10 +226,45 @@ class Clocks(object):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class Prefetcher(object):
+    """Background host worker: batch dict -> prepare_pretrain -> pinned staging buffers, one step ahead (the reference
+    overlaps collate with compute the same way: DataLoader workers + PrefetchLoader, P/data/loader.py:62-130)."""
+
+    def __init__(self, batches, pad, depth=2):
+        import queue
+        self.batches, self.pad = batches, pad
+        self.q = queue.Queue(maxsize=depth)
+        self.n = 0
+        self.stop = False
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        from vln_goat_b200 import batching
+        i = 0
+        while not self.stop:
+            task = TASKS[i % 3]
+            b = self.batches[(i // 3) % len(self.batches)]
+            P = batching.pin(batching.prepare_pretrain(b, task, pad=self.pad))
+            while not self.stop:
+                try:
+                    self.q.put((task, P), timeout=0.1)
+                    break
+                except Exception:
+                    continue
+            i += 1
+
+    def get(self):
+        return self.q.get()
+
+    def close(self):
+        self.stop = True
+
+
 def run_goat(args):
     import torch
     import torch.distributed as dist
-    from vln_goat_b200 import engine, ops, runtime, workloads
+    from vln_goat_b200 import batching, engine, ops, pretrain_model, runtime, workloads
     from vln_goat_b200.config import GoatConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,19 +280,44 @@ def run_goat(args):
     cdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     runtime.set_compute_dtype(cdt)
 
-    torch.manual_seed(0)  # same initial weights on every rank, as DDP's broadcast would give
-    model = workloads.C2CrossEncoder(GoatConfig()).to(dev).train()
+    model = pretrain_model.GlocalTextPathCMTPreTraining(GoatConfig(pretrain_tasks=TASKS))
+    model.load_state_dict(oracle_params(), strict=True)     # same seeded weights on every rank (and in the oracle)
+    model.tie_weights()
+    model = model.to(dev).train()
+    pad = batching.PadSpec()
 
-    def loss_fn(txt, tm, vp, vm):
-        t, v = model(txt, tm, vp, vm)
-        return workloads.c2_loss(t, v)
+    host = [workloads.synthetic_pretrain_batch(B, L, seed=1000 + 17 * rank + i) for i in range(N_BATCHES)]
 
-    host = [tuple(t.pin_memory() for t in b) for b in make_batches(4, B, seed=1000 + rank)]
-    devb = [tuple(t.to(dev) for t in b) for b in host]
-    active = engine.active_parameters(model, loss_fn, devb[0])
+    def loss_fn_of(task):
+        return lambda P: model.scalar_loss(P, task)
+
+    def to_dev(P):
+        return {k: v.to(dev, non_blocking=True) for k, v in P.items()}
+
+    # parameters any task trains (the reference's AdamW never touches the rest: their grad stays None)
+    active, seen = [], set()
+    for task in TASKS:
+        P0 = to_dev(batching.prepare_pretrain(host[0], task, pad=pad))
+        for p in engine.active_parameters(model, loss_fn_of(task), (P0,)):
+            if id(p) not in seen:
+                seen.add(id(p))
+                active.append(p)
     flat = engine.FlatParams(model, shadow_dtype=cdt if cdt != torch.float32 else None, only=active)
-    ts = engine.TrainStep(flat, loss_fn, devb[0], use_graph=not args.no_graph, **OPT)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    if cdt == torch.float16:
+        flat.enable_loss_scale()
+    ts = engine.TrainStep(flat, use_graph=not args.no_graph, check_unwritten=False, **OPT)
+
+    # device-resident prepared batches; one captured graph per (task, padded-shape signature)
+    resident = []
+    for i in range(N_BATCHES):
+        for task in TASKS:
+            P = to_dev(batching.prepare_pretrain(host[i], task, pad=pad))
+            key = (task, engine.input_signature(P))
+            if not ts.has(key):
+                ts.capture(key, loss_fn_of(task), P)
+            resident.append((task, key, P))
+    torch.cuda.synchronize()
+    n_graphs = len(ts.entries)
 
     def barrier():
         if world > 1:
@@ -246,121 +337,279 @@ def run_goat(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    # ---- device-resident: inputs already in HBM (rotating through 4 resident batches, D2D into the graph's inputs)
-    def step_resident(i):
-        ts.step(devb[i % len(devb)])
+    launches = [0]
 
-    for i in range(args.warmup):
+    def step_resident(i):
+        task, key, P = resident[i % len(resident)]
+        ts.step(P, key)
+        launches[0] += ts.launches_per_step
+
+    for i in range(max(args.warmup, 3)):
         step_resident(i)
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
+    launches[0] = 0
     ms = timed(step_resident, args.steps)
     value = world * args.steps / (ms / 1e3)
+    gpu_launches = launches[0]
 
-    # ---- end to end: batch in pinned host memory -> H2D on a copy stream (overlapping the previous step) -> step
-    #      -> loss D2H into pinned memory every step
+    # ---- end to end: host batch dict -> index builders + padding -> pinned -> H2D on a copy stream -> step -> loss D2H
+    pf = Prefetcher(host, pad)
     copy_stream = torch.cuda.Stream()
-    stage = [tuple(torch.empty_like(t) for t in devb[0]) for _ in range(2)]
+    losses = torch.zeros(args.steps + max(args.warmup, 3) + 4, dtype=torch.float32).pin_memory()
+    state = {"n": 0, "h2d": 0}
+    slots = [None, None]
     ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    losses = torch.zeros(args.steps + args.warmup + 1, dtype=torch.float32).pin_memory()
-    state = {"n": 0}
 
-    def prefetch(i):
+    def stage(i):
+        task, P = pf.get()
         s = i % 2
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s])
-            for d, h in zip(stage[s], host[i % len(host)]):
-                d.copy_(h, non_blocking=True)
+            d = {k: v.to(dev, non_blocking=True) for k, v in P.items()}
             ready[s].record(copy_stream)
+        slots[s] = (task, P, d)
+        state["h2d"] = batching.h2d_bytes(P)
 
     def step_e2e(i):
         s = i % 2
+        task, P, d = slots[s]
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[s])
-        ts.load_inputs(stage[s])
-        consumed[s].record(cur)
-        prefetch(i + 1)
-        loss = ts.step()
+        key = (task, engine.input_signature(d))
+        if not ts.has(key):
+            ts.capture(key, loss_fn_of(task), d)     # an unseen padded shape: capture once (none in this run's set)
+        ts.load_inputs(d, key)
+        for v in d.values():
+            v.record_stream(cur)
+        stage(i + 1)
+        loss = ts.step(None, key)
         losses[state["n"]:state["n"] + 1].copy_(loss.reshape(1), non_blocking=True)
         state["n"] += 1
 
-    for s in range(2):
-        consumed[s].record(torch.cuda.current_stream())
-    prefetch(0)
-    for i in range(args.warmup):
+    stage(0)
+    wu = max(args.warmup, 3)
+    for i in range(wu):
         step_e2e(i)
-    off = args.warmup
-    ms_e2e = timed(lambda i: step_e2e(i + off), args.steps)
+    ms_e2e = timed(lambda i: step_e2e(i + wu), args.steps)
     e2e = world * args.steps / (ms_e2e / 1e3)
-    clk = clocks.stop() if rank == 0 else None
+    pf.close()
     torch.cuda.synchronize()
     lv = losses[:state["n"]]
     if not bool(torch.isfinite(lv).all()):
         raise RuntimeError("non-finite loss in the timed run: %s" % lv.tolist())
 
+    # ---- sustained: the device-resident loop for >= 2 s
+    sustained = None
+    if not args.no_extras:
+        n_s = max(args.steps, int(2.2 * value / world) // 3 * 3 + 3)
+        ms_s = timed(step_resident, n_s)
+        sustained = {"steps": n_s, "seconds": ms_s / 1e3, "value": world * n_s / (ms_s / 1e3), "unit": "steps/s"}
+    clk = clocks.stop() if rank == 0 else None
+
+    if args.selfcheck and world > 1:
+        selfcheck(torch, dist, model, flat, resident, dev, rank)
+
     if rank == 0:
-        roof = gemm_roofline(torch, ops, ts, cdt, ms / args.steps)
-        roof_attn = attention_roofline(torch, ops, cdt, ms / args.steps)
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "C2: 6 RobertaLayer + 3 BertCrossLayer fwd+bwd+clip+AdamW, hidden 768, 80 tok x 37 view tokens",
-                       "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
-                       "dropout": 0.1, "cuda_graph": not args.no_graph,
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
+                       "dropout": 0.1, "cuda_graph": not args.no_graph, "captured_graphs": n_graphs,
+                       "padding": "S (trajectory steps) to x32, G (map nodes) to x8, masked tokens to x128",
+                       "loss_scale": "dynamic (device-resident GradScaler semantics)" if cdt == torch.float16 else None,
+                       "params_trained": int(flat.numel),
                        "l2": "per-step working set (%.0f MB params/grads/moments + activations) exceeds the 126 MB L2; "
-                             "4 rotating input batches" % (flat.numel * 4 * 4 / 1e6),
+                             "%d rotating batches per task" % (flat.numel * 4 * 4 / 1e6, N_BATCHES),
                        "loss_first_last": [float(lv[0]), float(lv[-1])]},
             "clocks": clk,
             "e2e": {"value": e2e, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": ts.launches_per_step * args.steps,
-            "gpu_launches_per_step": ts.launches_per_step,
-            "roofline": roof,
-            "roofline_attention": roof_attn,
+                    "h2d_bytes_per_step": state["h2d"], "d2h_bytes_per_step": 4,
+                    "host_work": "batching.prepare_pretrain (index builders + padding) + pinned staging on a worker thread"},
+            "gpu_launches": gpu_launches,
+            "gpu_launches_per_step": gpu_launches / float(args.steps),
+            "sustained": sustained,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores = time_cpu(2, 1, 16)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                    "sample": "2 timed steps on a 16-sample slice of the batch-64 step, scaled by 16/64; "
-                                              "oracle/ restatement of the reference modules, torch fp32, %d threads" % cores}
+        if flat.scaler is not None:
+            sc = flat.scaler.cpu().tolist()
+            line["config"]["loss_scale_state"] = {"scale": sc[0], "skipped_steps": sc[3], "steps_taken": sc[4]}
+        if not args.no_extras:
+            line["parity_max_err"] = parity(torch, model, host[0], dev, cdt)
+            line["roofline"] = gemm_roofline(torch, ops, ts, resident, ms / args.steps)
+            line["roofline_attention"] = attention_roofline(torch, ops, ts, resident, cdt, ms / args.steps)
+            if world == 1:
+                line["eager_b200_baseline"] = eager_baseline(torch, host, dev)
+                line["c2"] = run_c2(torch, cdt, dev)
+                if not args.no_cpu_baseline:
+                    v, dt, cores, n = time_cpu(3, 0)
+                    line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                                            "sample": "3 timed optimizer steps (one per task MLM/SAP/CFP) at the FULL batch 64; "
+                                                      "oracle/ restatement of the reference model, torch fp32, %d threads" % cores}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def gemm_roofline(torch, ops, ts, cdt, step_ms):
-    """Re-time every GEMM launch of one step (shapes recorded from the real step) with CUDA events."""
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = peaks.get("bf16_tflops_sustained")
-    which = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-    if peak is None:
-        peak, which = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
-    rec = []
-    ops.GEMM_LOG = rec
-    ts._fwd_bwd()  # eager pass: records (M,N,K,a_mn,b_mn) per launch and warms every shape
-    ops.GEMM_LOG = None
+def selfcheck(torch, dist, model, flat, resident, dev, rank):
+    """After the sharded optimizer steps of the run every rank must hold bit-identical parameters (fp32 masters of what
+    the kernels read in fp32, 16-bit shadow of the rest) and compute bit-identical forward outputs."""
+    import hashlib
+    flat.sync_master()
     torch.cuda.synchronize()
-    ts.flat.g.zero_()
+    h = hashlib.sha256(flat.p[:flat.numel].cpu().numpy().tobytes())
+    if flat.shadow is not None:
+        h.update(flat.shadow[:flat.numel].view(torch.int16).cpu().numpy().tobytes())
+    model.eval()
+    with torch.no_grad():
+        for task in TASKS:
+            src = [r for r in resident if r[0] == task][0][2]
+            if rank != 0:
+                src = {k: torch.empty_like(v) for k, v in src.items()}
+            for k in sorted(src):
+                dist.broadcast(src[k], src=0)
+            out = model.forward_prepared(src, task, compute_loss=False)
+            for o in (out if isinstance(out, tuple) else (out,)):
+                if torch.is_floating_point(o):
+                    h.update(o.float().cpu().numpy().tobytes())
+    model.train()
+    digest = int(h.hexdigest()[:15], 16)
+    t = torch.tensor([digest], device=dev, dtype=torch.int64)
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if int(lo) != int(hi):
+        raise RuntimeError("selfcheck: ranks hold different parameters / outputs after the data-parallel steps")
+    if rank == 0:
+        print("selfcheck ok: identical parameters and forward outputs on all ranks (digest %x)" % digest, file=sys.stderr)
+
+
+def parity(torch, model, batch, dev, cdt):
+    """Eval-mode forward of the benchmarked model (same dtype, same batch size 64) against the CPU oracle."""
+    from oracle import goat_pretrain_oracle as PO
+    from vln_goat_b200 import batching
+    torch.set_num_threads(os.cpu_count() or 1)
+    Pr = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    model.eval()
+    errs = {}
+
+    def rel(got, ref):
+        got, ref = got.detach().float().cpu(), ref.float()
+        fin = torch.isfinite(ref)
+        if not torch.equal(torch.isfinite(got), fin):
+            return float("inf")
+        return float((got[fin] - ref[fin]).abs().max() / max(1.0, float(ref[fin].abs().max()))) if fin.any() else 0.0
+    with torch.no_grad():
+        for task in TASKS:
+            P = {k: v.to(dev) for k, v in batching.prepare_pretrain(batch, task, pad=batching.PadSpec()).items()}
+            out = model.forward_prepared(P, task, compute_loss=False)
+            loss = model.forward_prepared(P, task, compute_loss=True)
+            if task == "mlm":
+                scores, rloss = PO.forward_mlm(Pr, batch)
+                n = scores.shape[0]
+                errs["mlm_scores"] = rel(out[:n], scores)
+                errs["mlm_loss"] = rel(loss[:n], rloss)
+            elif task == "sap":
+                gl, ll, fl, rloss = PO.forward_sap(Pr, batch)
+                G_ = gl.shape[1]
+                errs["sap_global_logits"] = rel(out[0][:, :G_], gl)
+                errs["sap_local_logits"] = rel(out[1], ll)
+                errs["sap_fused_logits"] = rel(out[2][:, :G_], fl)
+                errs["sap_loss"] = rel(loss, rloss)
+            else:
+                go, vo, fo, to, rloss = PO.forward_cfp(Pr, batch)
+                for nm, a, b in (("cfp_gmap", out[0], go), ("cfp_vp", out[1], vo), ("cfp_fused", out[2], fo), ("cfp_txt", out[3], to)):
+                    errs[nm] = rel(a, b)
+                errs["cfp_loss"] = rel(loss, rloss)
+    model.train()
+    errs["max"] = max(errs.values())
+    errs["tolerance"] = 1e-5 if cdt == torch.float32 else 1e-3
+    errs["reference"] = "oracle/goat_pretrain_oracle.py (fp32, CPU), same parameters after the timed steps, batch 64, eval mode"
+    return errs
+
+
+def eager_baseline(torch, host, dev):
+    """The reference-style eager path ON the B200: the oracle restatement (plain torch ops, Python aggregation loops,
+    per-tensor AdamW) with .cuda() tensors, fp32 and autocast fp16."""
+    out = {}
+    dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host[:2]]
+    for name, ac in (("fp32", False), ("autocast_fp16", True)):
+        try:
+            step = oracle_step_fn(dev, autocast=ac)
+            for i in range(3):
+                step(dev_batches[i % 2], TASKS[i % 3])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = 6
+            for i in range(n):
+                step(dev_batches[i % 2], TASKS[i % 3])
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n
+            out[name] = {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": dt * 1e3}
+        except Exception as e:       # noqa: BLE001 -- a baseline that cannot run is reported, not fatal
+            out[name] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    out["what"] = ("oracle/ restatement of the reference model run eagerly on the same B200 (torch ops, Python loops of the "
+                   "reference kept), 6 timed steps, batch 64, wall clock with synchronize")
+    return out
+
+
+def _time_graph(torch, fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del g
+    return ms
+
+
+def _record_round(torch, ops, ts, resident, what):
+    """eager fwd+bwd of one MLM + SAP + CFP round with the launch log on -> list of records"""
+    rec = []
+    setattr(ops, what, rec)
+    done = set()
+    for task, key, P in resident:
+        if task in done:
+            continue
+        done.add(task)
+        ts.load_inputs(P, key)
+        ts._fwd_bwd(ts.entries[key])
+    setattr(ops, what, None)
+    torch.cuda.synchronize()
+    ts.flat.zero_grad()
+    return rec
+
+
+def gemm_roofline(torch, ops, ts, resident, step_ms):
+    """Re-time every GEMM launch of one MLM + SAP + CFP round (shapes recorded from the real steps) with CUDA events."""
+    pk = peaks()
+    peak = pk.get("bf16_tflops")
+    which = "MEASURED_PEAKS.json bf16_tflops (burst: each launch group is timed alone)"
+    if peak is None:
+        peak, which = 1650.0, "fallback (B200_PROFILING.md burst ~1.65 PFLOP/s)"
+    rec = _record_round(torch, ops, ts, resident, "GEMM_LOG")
     uniq = {}
     for r in rec:
         uniq[r] = uniq.get(r, 0) + 1
     dev = torch.device("cuda", torch.cuda.current_device())
-    tot_ms, tot_flop = 0.0, 0.0
-    umma_ms, umma_flop, n_umma = 0.0, 0.0, 0
+    umma_ms, umma_flop, n_umma, simt_ms = 0.0, 0.0, 0, 0.0
     for (M, N, K, a_mn, b_mn, dt_, simt, acc_, act, has_bias, has_res, out32, has_drop, has_out2), cnt in uniq.items():
         dt_t = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}[dt_]
-        A = torch.randn((K, M) if a_mn else (M, K), device=dev).to(dt_t)
-        Bm = torch.randn((K, N) if b_mn else (N, K), device=dev).to(dt_t)
+        A = (torch.randn((K, M) if a_mn else (M, K), device=dev) * 0.05).to(dt_t)
+        Bm = (torch.randn((K, N) if b_mn else (N, K), device=dev) * 0.05).to(dt_t)
         out = (torch.zeros if acc_ else torch.empty)((M, N), device=dev, dtype=torch.float32 if out32 else dt_t)
         kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), out=out, accumulate=bool(acc_), act=act)
         if has_bias:
@@ -375,114 +624,107 @@ def gemm_roofline(torch, ops, ts, cdt, step_ms):
             kw["aux_out"] = torch.empty((M, N), device=dev, dtype=dt_t)
         if act in (ops.ACT_DGELU, ops.ACT_DRELU):
             kw["aux_in"] = torch.randn(M, N, device=dev).to(dt_t)
-
-        def launch():
-            ops.gemm(A, Bm, **kw)
-        for _ in range(3):
-            launch()
-        reps = 20
-        # `reps` launches captured in one CUDA graph: the event pair sees device time, not the ~20 us of Python /
-        # ctypes / tensor-map encoding per call (the step itself is replayed as a graph, too)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(reps):
-                launch()
-        g.replay()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        del g
-        fl = 2.0 * M * N * K
-        tot_ms += ms * cnt
-        tot_flop += fl * cnt
-        if not simt:
+        ms = _time_graph(torch, lambda: ops.gemm(A, Bm, **kw))
+        if simt:
+            simt_ms += ms * cnt
+        else:
             umma_ms += ms * cnt
-            umma_flop += fl * cnt
+            umma_flop += 2.0 * M * N * K * cnt
             n_umma += cnt
     achieved = umma_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
-    # DRAM bytes moved by the same launches, from the committed ncu pass over one step (profiles/r01d_*)
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")) as f:
-            tj = json.load(f)
-        if tj.get("gemm_launches") == n_umma:
-            traffic = tj["gemm_dram_bytes_per_step"]
-            traffic_src = ("profiles/r01d_launches_one_step.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
-                           "%d GEMM launches of one step (ncu, cold cache)" % n_umma)
-    except Exception:
-        pass
-    return {"bound": "tensor", "kernel": "gemm_umma2_kernel / gemm_umma_kernel (tcgen05.mma cta_group::2 + TMA; all %d tensor-core GEMM launches of one step, "
-                      "each shape re-timed as 20 graph-captured launches)" % n_umma,
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_unit": "bytes per step over the same launches", "traffic_source": traffic_src,
-            "peak_source": which, "flop_per_step": umma_flop, "gemm_ms_per_step": umma_ms,
-            "gemm_share_of_step": umma_ms / step_ms if step_ms else None,
-            "step_tflops": umma_flop / (step_ms * 1e-3) / 1e12 if step_ms else None}
+    round_ms = 3.0 * step_ms
+    return {"bound": "tensor", "kernel": "gemm_umma2_kernel / gemm_umma_kernel (tcgen05.mma cta_group::2 + TMA; all %d tensor-core GEMM "
+                                          "launches of one MLM+SAP+CFP round, each shape re-timed as 20 graph-captured launches)" % n_umma,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": which, "flop_per_round": umma_flop, "gemm_ms_per_round": umma_ms, "simt_gemm_ms_per_round": simt_ms,
+            "gemm_share_of_step": umma_ms / round_ms if round_ms else None,
+            "step_tflops": umma_flop / (round_ms * 1e-3) / 1e12 if round_ms else None}
 
 
-def attention_roofline(torch, ops, cdt, step_ms):
+def attention_roofline(torch, ops, ts, resident, cdt, step_ms):
     """The other regime of SURVEY.md 8d: the attention core (QK^T, softmax, PV and its backward) is HBM / latency
-    bound.  Algorithmic bytes of the step's 24 attention launches / their device time (20 graph-captured launches each)."""
+    bound.  Algorithmic bytes of the attention launches of one round / their device time."""
     if cdt == torch.float32:
         return None
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs")
+    pk = peaks()
+    peak = pk.get("hbm_gbs")
     which = "MEASURED_PEAKS.json hbm_gbs"
     if peak is None:
         peak, which = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    rec = _record_round(torch, ops, ts, resident, "ATTN_LOG")
+    uniq = {}
+    for r in rec:
+        uniq[r] = uniq.get(r, 0) + 1
     dev = torch.device("cuda", torch.cuda.current_device())
-    heads, p_drop = 12, 0.1
-
-    def graph_ms(fn, reps=20):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(reps):
-                fn()
-        g.replay()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
+    heads = 12
     tot_ms, tot_bytes, n = 0.0, 0.0, 0
-    # (count per step, Nq, Nk): 6 text self-attentions, 3 view self-attentions, 3 view -> text cross-attentions
-    for cnt, Nq, Nk in ((6, L, L), (3, NQ, NQ), (3, NQ, L)):
-        q = torch.randn(B, Nq, H, device=dev).to(cdt)
-        k = torch.randn(B, Nk, H, device=dev).to(cdt)
-        v = torch.randn(B, Nk, H, device=dev).to(cdt)
-        km = torch.zeros(B, Nk, device=dev)
-        w = torch.randn(B, Nq, H, device=dev).to(cdt)
-        o, lse = ops.attn_fwd(q, k, v, heads, km, drop_p=p_drop, drop_seed=3)
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        f_ms = graph_ms(lambda: ops.attn_fwd(q, k, v, heads, km, drop_p=p_drop, drop_seed=3))
-        b_ms = graph_ms(lambda: ops.attn_bwd(w, q, k, v, o, lse, heads, dq, dk, dv, km, drop_p=p_drop, drop_seed=3))
-        f_bytes = 2.0 * B * H * (2 * Nq + 2 * Nk) + 4.0 * B * Nk          # q, o + k, v (16-bit) + key mask
-        b_bytes = 2.0 * B * H * (4 * Nq + 4 * Nk) + 4.0 * B * Nk          # q, o, dO, dQ + k, v, dK, dV
-        tot_ms += cnt * (f_ms + b_ms)
-        tot_bytes += cnt * (f_bytes + b_bytes)
-        n += 2 * cnt
-    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "attn_fwd_pipe_kernel + attn_bwd_pipe_kernel (all %d attention launches of one step, "
-                                      "dropout 0.1, each shape re-timed as 20 graph-captured launches)" % n,
+    for (kind, Bn, Nq, Nk, has_bias, p_drop), cnt in uniq.items():
+        q = torch.randn(Bn, Nq, H, device=dev).to(cdt)
+        k = torch.randn(Bn, Nk, H, device=dev).to(cdt)
+        v = torch.randn(Bn, Nk, H, device=dev).to(cdt)
+        km = torch.zeros(Bn, Nk, device=dev)
+        bias = torch.zeros(Bn, Nq, Nk, device=dev) if has_bias else None
+        o, lse = ops.attn_fwd(q, k, v, heads, km, bias, drop_p=p_drop, drop_seed=3)
+        if kind == "fwd":
+            ms = _time_graph(torch, lambda: ops.attn_fwd(q, k, v, heads, km, bias, drop_p=p_drop, drop_seed=3))
+            nbytes = 2.0 * Bn * H * (2 * Nq + 2 * Nk) + 4.0 * Bn * Nk + (4.0 * Bn * Nq * Nk if has_bias else 0.0)
+        else:
+            w = torch.randn(Bn, Nq, H, device=dev).to(cdt)
+            dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+            ms = _time_graph(torch, lambda: ops.attn_bwd(w, q, k, v, o, lse, heads, dq, dk, dv, km, bias, drop_p=p_drop,
+                                                          drop_seed=3, want_dbias=bool(has_bias)))
+            nbytes = 2.0 * Bn * H * (4 * Nq + 4 * Nk) + 4.0 * Bn * Nk + (8.0 * Bn * Nq * Nk if has_bias else 0.0)
+        tot_ms += cnt * ms
+        tot_bytes += cnt * nbytes
+        n += cnt
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    round_ms = 3.0 * step_ms
+    return {"bound": "hbm", "kernel": "attention core kernels (all %d launches of one MLM+SAP+CFP round, dropout as run, each shape "
+                                      "re-timed as 20 graph-captured launches)" % n,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": which, "bytes_per_step": tot_bytes, "attention_ms_per_step": tot_ms,
-            "attention_share_of_step": tot_ms / step_ms if step_ms else None}
+            "peak_source": which, "bytes_per_round": tot_bytes, "attention_ms_per_round": tot_ms,
+            "attention_share_of_step": tot_ms / round_ms if round_ms else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# second line: BASELINE.json configs[1] (the round-1 headline): 6 RobertaLayer + 3 BertCrossLayer, batch 64
+# ------------------------------------------------------------------------------------------------
+def run_c2(torch, cdt, dev, steps=60):
+    from vln_goat_b200 import engine, workloads
+    from vln_goat_b200.config import GoatConfig
+    torch.manual_seed(0)
+    model = workloads.C2CrossEncoder(GoatConfig()).to(dev).train()
+
+    def loss_fn(txt, tm, vp, vm):
+        t, v = model(txt, tm, vp, vm)
+        return workloads.c2_loss(t, v)
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for _ in range(4):
+        txt = torch.randn(B, L, H, generator=g)
+        vp = torch.randn(B, NQ, H, generator=g)
+        vp[:, 0] = 0.0
+        lens = torch.randint(L // 2, L + 1, (B,), generator=g)
+        lens[0] = L
+        tm = torch.arange(L)[None, :] < lens[:, None]
+        batches.append(tuple(t.to(dev) for t in (txt, tm, vp, torch.ones(B, NQ, dtype=torch.bool))))
+    active = engine.active_parameters(model, loss_fn, batches[0])
+    flat = engine.FlatParams(model, shadow_dtype=cdt if cdt != torch.float32 else None, only=active)
+    if cdt == torch.float16:
+        flat.enable_loss_scale()
+    ts = engine.TrainStep(flat, loss_fn, batches[0], **OPT)
+    for i in range(5):
+        ts.step(batches[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ts.step(batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "C2: 6 RobertaLayer + 3 BertCrossLayer fwd+bwd+clip+AdamW (70.9 M params), batch 64, device-resident",
+            "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps, "gpu_launches_per_step": ts.launches_per_step}
 
 
 def main():

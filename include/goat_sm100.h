@@ -200,12 +200,19 @@ int goat_dropout_cast(const void* src, int src_dtype, void* dst, int dst_dtype, 
  *               max_grad_norm (<=0: off), grad pre-scale}; norm_out (optional, device) receives the norm.
  *               zero_grad=1 also clears g (optimizer.zero_grad(), P/train_r2r_goat.py:366) so that the next
  *               step's split-K weight-gradient GEMMs can accumulate into it with atomics.
+ *   scaler (optional, DEVICE array of 5 floats {scale, clean steps, overflowed, skipped, steps taken}): the dynamic loss
+ *               scale of the fp16 path -- torch.cuda.amp.GradScaler in the reference (P/train_r2r_goat.py:279,325,
+ *               351-363).  Gradients are additionally divided by scaler[0]; a non-finite norm SKIPS the update (only
+ *               g is cleared); bias corrections come from scaler[4] + 1.  goat_scaler_update (one thread) then
+ *               applies GradScaler.update(): scale *= backoff after an overflow, *= growth after `interval` clean steps.
  * ------------------------------------------------------------------------------------------ */
 size_t goat_sumsq_workspace_bytes(void);
 int goat_sumsq(const float* g, long long n, float* partial, int* nparts_out, goat_stream_t stream);
 int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
                     long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
-                    int zero_grad, goat_stream_t stream);
+                    int zero_grad, const float* scaler, goat_stream_t stream);
+int goat_scaler_update(float* scaler, const float* partial, int nparts, float growth, float backoff, int interval,
+                       goat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention pooling over the token axis of x [B,N,H] (fp32), softmax WITHOUT a mask (the reference pools over
@@ -215,11 +222,14 @@ int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int sh
  *   mode 1  CFP pooling               P/model/pretrain_goat.py:502-515, M/models/vilmodel_GOAT.py:905-918:
  *           s_n = tanh(x_n) . w;            a = softmax_n(s);  out = tanh(sum_n a_n x_n)
  * fwd saves a [B,N] (and s [B,N] in mode 0).  bwd: dx [B,N,H] written; dw [H] and db [1] ACCUMULATED (caller zeroes).
+ * n_valid (optional DEVICE int): pool over the first min(N, *n_valid) tokens only -- the reference pools over the
+ * batch's own padded length, so buffers padded further (static shapes for CUDA graphs) must not add tokens.
  * ------------------------------------------------------------------------------------------ */
 int goat_attn_pool_fwd(const float* x, const float* w, const float* bias, int mode, int B, int N, int H, float* out,
-                       float* a, float* s, goat_stream_t stream);
+                       float* a, float* s, const int* n_valid, goat_stream_t stream);
 int goat_attn_pool_bwd(const float* dout, const float* x, const float* w, const float* a, const float* s, const float* out,
-                       int mode, int B, int N, int H, float* dx, float* dw, float* db, goat_stream_t stream);
+                       int mode, int B, int N, int H, float* dx, float* dw, float* db, const int* n_valid,
+                       goat_stream_t stream);
 
 /* p(z)-weighted dictionary sum of the back-door adjustment: out[b,:] = sum_n p[b,n] x[b,n,:]
  * (M/models/vilmodel_GOAT.py:664-665 image z-dict, :107-111 instruction z-dicts).  p is data (no gradient). */
@@ -264,6 +274,19 @@ int goat_embed_fwd(const long long* ids, const float* word, const float* pos, co
                    float* out, goat_stream_t stream);
 int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, long long padding_idx, float* dword,
                    float* dpos, float* dtype, goat_stream_t stream);
+
+/* Backward of the activation behind a head / pooler nn.Linear (ClsPrediction ReLU, BertPooler tanh, the GELU of the
+ * MLM / CFP transforms: P/model/pretrain_goat.py:27-38, P/model/Bert_backbone.py:783-811):
+ *   out[i] = dy[i] * act'(ref[i]) converted to out_dtype, one pass.  ref = the forward OUTPUT y (fp32) for RELU / TANH
+ *   (y > 0, 1 - y^2) and the stored pre-activation (ref_dtype) for GELU.  act: GOAT_ACT_RELU / _TANH / _GELU / _NONE. */
+int goat_act_grad(const float* dy, const void* ref, int ref_dtype, int act, void* out, int out_dtype, long long n,
+                  goat_stream_t stream);
+
+/* Spatial-relation bias of the global-map self-attention: sprel_linear = nn.Linear(1, 1) applied to every pairwise
+ * distance (P/model/vilmodel_goat.py:499-501, M/models/vilmodel_GOAT.py:473-476): out[i] = d[i] * w[0] + b[0].
+ * bwd: dw[0] += sum dout[i] d[i], db[0] += sum dout[i]  (ACCUMULATED; the distances are data). */
+int goat_sprel_fwd(const float* d, const float* w, const float* b, float* out, long long n, goat_stream_t stream);
+int goat_sprel_bwd(const float* dout, const float* d, float* dw, float* db, long long n, goat_stream_t stream);
 
 #ifdef __cplusplus
 }

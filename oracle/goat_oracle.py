@@ -56,7 +56,7 @@ def gen_seq_masks(lens, max_len=None):
     """P/model/ops.py:36-44."""
     if max_len is None:
         max_len = int(max(lens))
-    return torch.arange(max_len)[None, :] < lens[:, None]
+    return torch.arange(max_len, device=lens.device)[None, :] < lens[:, None]
 
 
 def attn_core(q, k, v, mask=None, num_heads=12):
@@ -170,7 +170,7 @@ def pano_layer(p, pre, x, key_padding_mask=None, num_heads=12, eps=1e-5):
     v = linear(x2, w[2 * H:], b[2 * H:])
     mask = None
     if key_padding_mask is not None:
-        mask = torch.zeros(key_padding_mask.shape, dtype=x.dtype)
+        mask = torch.zeros(key_padding_mask.shape, dtype=x.dtype, device=x.device)
         mask = mask.masked_fill(key_padding_mask, float("-inf"))[:, None, None, :]
     ctx = attn_core(q, k, v, mask, num_heads)
     x = x + linear(ctx, p[pre + "self_attn.out_proj.weight"], p[pre + "self_attn.out_proj.bias"])
@@ -222,7 +222,7 @@ def infonce_sym(a, b, temperature=1.0):
     """Symmetric InfoNCE over in-batch negatives: (CE(sim) + CE(sim^T)) / 2 per row.
     P/model/pretrain_goat.py:519-534."""
     sim = (a @ b.transpose(0, 1)) / temperature
-    tgt = torch.arange(a.shape[0])
+    tgt = torch.arange(a.shape[0], device=a.device)
     return (cross_entropy_rows(sim, tgt) + cross_entropy_rows(sim.transpose(0, 1), tgt)) / 2.0
 
 

@@ -180,8 +180,12 @@ def test_segment_reduce_and_embed():
 # ----------------------------------------------------------------------------------------------
 # full models vs the reference fixtures
 # ----------------------------------------------------------------------------------------------
-FULL_TOL = {torch.float32: 5e-5, torch.bfloat16: 3e-2}
-FULL_DIG = {torch.float32: 1e-4, torch.bfloat16: 5e-2}
+# BASELINE.json north_star: action logits, CFP embeddings, MLM scores within 1e-3 (fp16) / 1e-5 (fp32) of the reference.
+# fp16 (10 mantissa bits) is the certified tensor-core dtype; bf16 (7 bits) is kept as a throughput-equivalent option
+# and cannot meet 1e-3 through ~15 stacked blocks (its bound here is 3e-2).
+FULL_TOL = {torch.float32: 1e-5, torch.float16: 1e-3, torch.bfloat16: 3e-2}
+FULL_DIG = {torch.float32: 1e-4, torch.float16: 1e-2, torch.bfloat16: 5e-2}
+FULL_DTYPES = [torch.float32, torch.float16, torch.bfloat16]
 
 
 def _seed_model(model, seed):
@@ -198,7 +202,7 @@ def _sub(gold, prefix):
     return {k[len(prefix):]: v for k, v in gold.items() if k.startswith(prefix)}
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", FULL_DTYPES)
 def test_pretrain_full_mlm_sap_cfp(dtype):
     from vln_goat_b200 import pretrain_model, runtime
     from vln_goat_b200.config import GoatConfig
@@ -252,7 +256,7 @@ def _nav_cfg():
                       use_lang2visn_attn=False, fix_lang_embedding=False, fix_pano_embedding=False, fix_local_branch=False)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", FULL_DTYPES)
 def test_nav_full_language_panorama_navigation(dtype):
     """BACL (text type_2 + image type_1) and FACL (text, vp, gmap) on: the three per-step modes chained."""
     from vln_goat_b200 import nav_model, runtime
@@ -285,7 +289,7 @@ def test_nav_full_language_panorama_navigation(dtype):
                    key_bias_atol=None if dtype == torch.float32 else 64.0)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", FULL_DTYPES)
 @pytest.mark.parametrize("kv_cache", [True, False])
 def test_nav_rollout_three_steps_vs_reference(dtype, kv_cache):
     """a teacher-forced rollout (language once, then panorama + navigation for three steps,
@@ -341,3 +345,207 @@ def test_vlnbert_wrapper_feature_dropout_and_modes():
         assert torch.isfinite(c).all() and not torch.equal(c, b)
         t = wrap("language", synth.batch_to(lang, "cuda"))
         assert t.shape == (2, 12, 768) and torch.isfinite(t).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# shape-static (padded) pretraining path, the full-model optimizer step, fp16 loss scaling
+# ----------------------------------------------------------------------------------------------
+def _pretrain_model(seed=20, train=False):
+    from vln_goat_b200 import pretrain_model
+    from vln_goat_b200.config import GoatConfig
+    cfg = GoatConfig(pretrain_tasks=("mlm", "sap", "cfp"))
+    if not train:
+        cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.0
+    model = _seed_model(pretrain_model.GlocalTextPathCMTPreTraining(cfg), seed)
+    model.tie_weights()
+    return model.cuda().eval()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_padded_prepared_batch_gives_the_same_rows(dtype):
+    """batching.prepare_pretrain with bucket padding (extra trajectory steps, map nodes, masked-token rows, index slots)
+    must not change any REAL row: logits / scores / pooled embeddings / losses equal the unpadded forward, which is the
+    reference's own batch layout (checked against the fixture above)."""
+    from vln_goat_b200 import batching, runtime
+    model = _pretrain_model()
+    batch = synth.pretrain_batch(B=3, L=24, seed=5)
+    pad = batching.PadSpec(S=16, G=16, NM=32, K=8, KF=8)
+    with runtime.compute(dtype), torch.no_grad():
+        for task in ("mlm", "sap", "cfp"):
+            P0 = synth.batch_to(batching.prepare_pretrain(batch, task, pad=None), "cuda")
+            P1 = synth.batch_to(batching.prepare_pretrain(batch, task, pad=pad), "cuda")
+            assert P1["view_fts"].shape[0] > P0["view_fts"].shape[0] and P1["gmap_step_ids"].shape[1] > P0["gmap_step_ids"].shape[1]
+            a = model.forward_prepared(P0, task, compute_loss=False)
+            b = model.forward_prepared(P1, task, compute_loss=False)
+            la = model.forward_prepared(P0, task, compute_loss=True)
+            lb = model.forward_prepared(P1, task, compute_loss=True)
+            if task == "mlm":
+                n = a.shape[0]
+                assert torch.equal(a, b[:n]) and torch.equal(la, lb[:n]) and float(lb[n:].abs().max()) == 0.0
+            elif task == "sap":
+                G = a[0].shape[1]
+                assert torch.equal(a[0], b[0][:, :G]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2][:, :G])
+                assert bool(torch.isinf(b[0][:, G:]).all()) and torch.equal(la, lb)
+            else:
+                for x, y in zip(a, b):
+                    assert torch.equal(x, y)
+                assert torch.equal(la, lb)
+            sa, sb = model.scalar_loss(P0, task), model.scalar_loss(P1, task)
+            assert abs(sa.item() - sb.item()) <= 1e-6 * max(1.0, abs(sa.item()))
+
+
+def _oracle_leaves(model):
+    P = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if v.is_floating_point()}
+    leaves = {k: v.requires_grad_(True) for k, v in P.items() if "decoder.weight" not in k}
+    full = dict(leaves)
+    full["mlm_head.predictions.decoder.weight"] = leaves["bert.embeddings.word_embeddings.weight"]
+    return leaves, full
+
+
+def test_full_model_flat_step_matches_oracle_adamw():
+    """One optimizer step of the FULL pretraining model through engine.FlatParams + engine.TrainStep (every parameter
+    gradient lands in the flat buffer, incl. the step-id embedding table and sprel_linear; captured graph replay; fused
+    clip + AdamW), for each task in turn, against the CPU oracle's autograd + per-tensor AdamW on the same batch (fp32
+    parity mode).  The gradient norm and the updated parameters must agree."""
+    from oracle import goat_pretrain_oracle as PO
+    from vln_goat_b200 import batching, engine, runtime
+    model = _pretrain_model()
+    batch = synth.pretrain_batch(B=3, L=24, seed=5)
+    opt = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_grad_norm=5.0)
+    with runtime.compute(torch.float32):
+        loss_fns = {t: (lambda P, t=t: model.scalar_loss(P, t)) for t in ("mlm", "sap", "cfp")}
+        preps = {t: synth.batch_to(batching.prepare_pretrain(batch, t, pad=batching.PadSpec(S=8, G=8, NM=16)), "cuda")
+                 for t in loss_fns}
+        active, seen = [], set()
+        for t, fn in loss_fns.items():
+            for p in engine.active_parameters(model, fn, (preps[t],)):
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    active.append(p)
+        leaves, full = _oracle_leaves(model)
+        flat = engine.FlatParams(model, only=active)
+        names = set(flat.names)
+        assert "bert.global_encoder.gmap_step_embeddings.weight" in names and "bert.global_encoder.sprel_linear.weight" in names
+        ts = engine.TrainStep(flat, check_unwritten=False, **opt)
+        M_ = {k: torch.zeros_like(v) for k, v in leaves.items()}
+        V_ = {k: torch.zeros_like(v) for k, v in leaves.items()}
+        nodecay = engine.NO_DECAY
+        used_ever = set()
+        for step, task in enumerate(("mlm", "sap", "cfp"), 1):
+            key = (task, engine.input_signature(preps[task]))
+            ts.capture(key, loss_fns[task], preps[task])
+            loss = ts.step(preps[task], key)
+            for v in leaves.values():
+                v.grad = None
+            ref_loss = PO.scalar_loss(full, batch, task)
+            ref_loss.backward()
+            assert abs(loss.item() - ref_loss.item()) < 2e-5 * max(1.0, abs(ref_loss.item()))
+            used_ever |= set(k for k, v in leaves.items() if v.grad is not None)
+            with torch.no_grad():
+                # the flat step updates every flattened parameter; parameters another task trains see a zero gradient
+                grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])) for k in flat.names}
+                norm, coef = O.clip_grad_norm(list(grads.values()), opt["max_grad_norm"])
+                for k in flat.names:
+                    wd = 0.0 if any(nd in k for nd in nodecay) else opt["weight_decay"]
+                    O.adamw_step(leaves[k], grads[k] * coef, M_[k], V_[k], step, opt["lr"], opt["betas"], opt["eps"], wd)
+            torch.cuda.synchronize()
+            assert abs(flat.grad_norm.item() - norm.item()) < 2e-4 * max(1.0, norm.item()), (task, flat.grad_norm.item(), norm.item())
+        got = dict(zip(flat.names, flat.params))
+        # Adam's first steps move a weight by ~lr * g / |g|: a gradient that is rounding noise on both sides (e.g. key biases)
+        # may legitimately differ in sign, so compare where the reference gradient history is not negligible
+        worst = 0.0
+        for k in flat.names:
+            d = (got[k].detach().cpu() - leaves[k].detach()).abs()
+            sig = V_[k].sqrt() > 1e-5
+            if sig.any():
+                worst = max(worst, d[sig].max().item())
+        assert worst < 2e-4, worst
+        assert used_ever == names, (sorted(used_ever ^ names)[:8])
+
+
+def test_fp16_loss_scale_skips_overflow_and_recovers():
+    """Device-resident GradScaler semantics (P/train_r2r_goat.py:279,325,351-363): an overflowing backward leaves the
+    parameters untouched, clears the gradients and halves the scale; clean steps update and, after the growth interval,
+    double it; the unscaled gradient norm matches the unscaled run."""
+    from vln_goat_b200 import engine
+    torch.manual_seed(0)
+    m = torch.nn.Linear(64, 32).cuda()
+    flat = engine.FlatParams(m, shadow_dtype=torch.float16)
+    flat.enable_loss_scale(init_scale=1024.0, growth_interval=2)
+    opt = dict(lr=1e-2, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0)
+    g = torch.randn(flat.numel, device="cuda")
+    p0 = flat.p.clone()
+    flat.g[:flat.numel].copy_(g * 1024.0)
+    flat.g[3] = float("inf")
+    flat.adamw_step(**opt)
+    torch.cuda.synchronize()
+    assert torch.equal(flat.p, p0) and float(flat.g.abs().max()) == 0.0
+    assert flat.scaler.tolist() == [512.0, 0.0, 1.0, 1.0, 0.0]
+    flat.g[:flat.numel].copy_(g * 512.0)
+    flat.adamw_step(**opt)
+    torch.cuda.synchronize()
+    assert abs(flat.grad_norm.item() - g.norm().item()) < 1e-4 * g.norm().item()
+    assert not torch.equal(flat.p, p0)
+    step1 = (flat.p[:flat.numel] - p0[:flat.numel]).abs()
+    assert abs(step1.max().item() - 1e-2) < 1e-4          # first Adam step: lr * sign(g), bias-corrected from scaler[4] + 1
+    assert flat.scaler.tolist() == [512.0, 1.0, 0.0, 1.0, 1.0]
+    flat.g[:flat.numel].copy_(g * 512.0)
+    flat.adamw_step(**opt)
+    torch.cuda.synchronize()
+    assert flat.scaler.tolist() == [1024.0, 0.0, 0.0, 1.0, 2.0]     # growth after 2 clean steps
+    assert torch.equal(flat.shadow[:flat.numel], flat.p[:flat.numel].half())
+
+
+def test_small_head_kernels_act_grad_sprel_gather():
+    from vln_goat_b200 import functional as Fn, ops
+    g = torch.Generator().manual_seed(4)
+    dy = torch.randn(37, 96, generator=g).cuda()
+    y = torch.randn(37, 96, generator=g).cuda()
+    for act, ref in ((ops.ACT_RELU, dy * (y > 0)), (ops.ACT_TANH, dy * (1 - y * y)),
+                     (ops.ACT_GELU, dy * (0.5 * (1 + torch.erf(y * 0.7071067811865476)) +
+                                          y * torch.exp(-0.5 * y * y) * 0.3989422804014327))):
+        assert maxerr(ops.act_grad(dy, y, act, torch.float32), ref) < 1e-5
+        assert maxerr(ops.act_grad(dy, y, act, torch.float16), ref.half()) < 4e-3
+    assert maxerr(ops.act_grad(dy, y.half(), ops.ACT_GELU, torch.float16).float(),
+                  dy * (0.5 * (1 + torch.erf(y.half().float() * 0.7071067811865476)) +
+                        y.half().float() * torch.exp(-0.5 * y.half().float() ** 2) * 0.3989422804014327)) < 4e-3
+    # sprel_linear: d * w + b, dw = sum(dout d), db = sum(dout)
+    d = (torch.rand(3, 9, 9, generator=g) * 10).cuda()
+    w = torch.tensor([[0.3]], device="cuda", requires_grad=True)
+    b = torch.tensor([-0.1], device="cuda", requires_grad=True)
+    wo = torch.randn(3, 9, 9, generator=g).cuda()
+    out = Fn.SprelFn.apply(d, w, b)
+    (out * wo).sum().backward()
+    assert maxerr(out, d * 0.3 - 0.1) < 1e-6
+    assert abs(w.grad.item() - (wo * d).sum().item()) < 1e-3 and abs(b.grad.item() - wo.sum().item()) < 1e-4
+    # embedding-row gather with the table gradient accumulated by the kernel
+    table = torch.randn(100, 768, generator=g).cuda().requires_grad_(True)
+    ids = torch.randint(0, 100, (3, 7), generator=g).cuda()
+    wo = torch.randn(3, 7, 768, generator=g).cuda()
+    out = Fn.GatherRowsFn.apply(ids, table)
+    (out * wo).sum().backward()
+    tr = table.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.embedding(ids, tr)
+    (ref * wo).sum().backward()
+    assert torch.equal(out, ref) and maxerr(table.grad, tr.grad) < 1e-5
+
+
+def test_attn_pool_n_valid_ignores_extra_padding():
+    from vln_goat_b200 import functional as Fn
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4, 24, 768, generator=g).cuda()
+    w = ((torch.rand(768, 1, generator=g) - 0.5) * 0.2).cuda()
+    wo = torch.randn(4, 768, generator=g).cuda()
+    nv = torch.tensor([17], dtype=torch.int32, device="cuda")
+    for mode, bias in ((1, None), (0, torch.tensor([0.05], device="cuda"))):
+        wv = (w if mode == 1 else w.t().contiguous()).clone().requires_grad_(True)
+        xa = x.clone().requires_grad_(True)
+        a = Fn.AttnPoolFn.apply(xa, wv, bias, mode, nv)
+        (a * wo).sum().backward()
+        wr = wv.detach().clone().requires_grad_(True)
+        xb = x[:, :17].clone().requires_grad_(True)
+        b = Fn.AttnPoolFn.apply(xb, wr, bias, mode, None)
+        (b * wo).sum().backward()
+        assert torch.equal(a, b)
+        assert maxerr(xa.grad[:, :17], xb.grad) < 1e-6 and float(xa.grad[:, 17:].abs().max()) == 0.0
+        assert maxerr(wv.grad, wr.grad) < 1e-5

@@ -205,3 +205,69 @@ def test_pretrain_checkpoint_remaps_into_the_finetune_model():
     missing = set(res.missing_keys)
     assert missing and all(any(t in k for t in ("z_", "do_img", "front_", "pooler", "local_his", "instr_", "concat_linear",
                                                  "img_after_linear")) for k in missing), sorted(missing)[:8]
+
+
+def _segment_reduce_cpu(src, idx, mean):
+    """what goat_segment_reduce_fwd computes (CPU restatement for the host-logic tests)"""
+    out = torch.zeros(idx.shape[0], src.shape[1])
+    for r in range(idx.shape[0]):
+        sel = [int(i) for i in idx[r] if i >= 0]
+        if sel:
+            out[r] = src[sel].sum(0) / (len(sel) if (mean and len(sel) > 1) else 1)
+    return out
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_prepare_pretrain_indices_reproduce_the_reference_loops(padded):
+    """batching.prepare_pretrain (index tensors, optional static padding) against the string-keyed loops of the reference
+    as restated in oracle/goat_pretrain_oracle.py: global-map aggregation, current-panorama selection, masked-token
+    selection and SAP logit fusion give the same numbers for the real rows, padded or not."""
+    from oracle import goat_oracle as O
+    from oracle import goat_pretrain_oracle as PO
+    from vln_goat_b200 import batching
+    batch = synth.pretrain_batch(B=5, L=24, seed=11)
+    pad = batching.PadSpec(S=8, G=8, NM=16, K=4, KF=4) if padded else None
+    H = 16
+    g = torch.Generator().manual_seed(0)
+    S, V = batch["traj_view_img_fts"].shape[:2]
+    views, fused = torch.randn(S, V, H, generator=g), torch.randn(S, H, generator=g)
+    ref = PO.aggregate_gmap(views, fused, batch)                                   # [B, G, H]
+    for task in ("mlm", "sap", "cfp"):
+        P = batching.prepare_pretrain(batch, task, pad=pad)
+        Sp = P["view_fts"].shape[0]
+        assert Sp % (8 if padded else 1) == 0 and Sp >= S
+        vp = torch.cat([views, torch.zeros(Sp - S, V, H)], 0)
+        fp = torch.cat([fused, torch.zeros(Sp - S, H)], 0)
+        B, G1, K = P["gmap_idx_v"].shape
+        got = _segment_reduce_cpu(vp.reshape(Sp * V, H), P["gmap_idx_v"].view(B * G1, K), True) + \
+            _segment_reduce_cpu(fp, P["gmap_idx_f"].view(B * G1, 1), False)
+        got = got.view(B, G1, H)
+        Gn = ref.shape[1]
+        assert torch.allclose(got[:, :Gn - 1], ref[:, 1:], atol=1e-6)
+        assert float(got[:, Gn - 1:].abs().max()) == 0.0 if G1 > Gn - 1 else True
+        assert int(P["n_gmap"]) == Gn and P["gmap_step_ids"].shape[1] == G1 + 1
+        # current panorama of every sample
+        last = (torch.tensor(batch["traj_step_lens"]).cumsum(0) - 1)
+        assert torch.equal(P["last_rows"].view(-1).long(), last)
+        assert torch.equal(P["view_lens"][:S], batch["traj_vp_view_lens"]) and bool((P["view_lens"][S:] == 1).all())
+    # masked tokens (row-major order of boolean indexing) and their labels; padded rows carry the ignore label
+    P = batching.prepare_pretrain(batch, "mlm", pad=pad)
+    sel = batch["txt_labels"] != -1
+    nm = int(sel.sum())
+    x = torch.randn(batch["txt_ids"].numel(), H, generator=g)
+    got = _segment_reduce_cpu(x, P["mlm_rows"], False)
+    assert torch.equal(got[:nm], x.view(*batch["txt_ids"].shape, H)[sel])
+    assert torch.equal(P["mlm_labels"][:nm], batch["txt_labels"][sel]) and bool((P["mlm_labels"][nm:] == -1).all())
+    assert abs(float(P["loss_inv"]) - 1.0 / nm) < 1e-7
+    # SAP logit fusion
+    P = batching.prepare_pretrain(batch, "sap", pad=pad)
+    B, Gp = P["gmap_visited_masks"].shape
+    Nq = P["vp_pos_fts"].shape[1]
+    gl, ll = torch.randn(B, Gp, generator=g), torch.randn(B, Nq, generator=g)
+    Gn = batch["gmap_step_ids"].shape[1]
+    ref = O.sap_fuse_logits(gl[:, :Gn], ll, batch["gmap_vpids"], batch["gmap_visited_masks"].tolist(),
+                            [c[-1] for c in batch["traj_cand_vpids"]], skip=1)
+    add = _segment_reduce_cpu(ll.reshape(-1, 1), P["fuse_idx"].view(B * Gp, -1), False).view(B, Gp)
+    assert torch.allclose((gl + add)[:, :Gn], ref, atol=1e-6)
+    assert float(add[:, Gn:].abs().max()) == 0.0 if Gp > Gn else True
+    assert bool(P["gmap_visited_masks"][:, Gn:].all()) if Gp > Gn else True

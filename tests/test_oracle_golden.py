@@ -138,3 +138,42 @@ def test_lang_encoder_do_tail_and_bacl_image():
     P = O.seeded_params(shapes, seed=9)
     out = O.bacl_image_type1(P, "", g["view"], g["zf"], g["pz"])
     assert maxerr(out, g["out"]) < TOL
+
+
+def test_pretrain_oracle_matches_reference_fixture():
+    """oracle/goat_pretrain_oracle.py (full MLM / SAP / CFP forward) vs the fixture the UNMODIFIED reference model produced
+    on the same seeded batch and seeded parameters (tests/golden/make_golden.py --tree pretrain_full)."""
+    from oracle import goat_pretrain_oracle as PO
+    from tests import synth
+    g = golden("pretrain_full")
+    keys = str(g["state_dict_keys"]).split("\n")
+    shapes = dict(pretrain_state_shapes())
+    assert set(keys) == set(shapes), (set(keys) ^ set(shapes))
+    P = O.seeded_params(shapes, seed=20)
+    # tied weights: load_state_dict copies both keys into the one shared tensor, the later key (the decoder's) stays
+    P["bert.embeddings.word_embeddings.weight"] = P["mlm_head.predictions.decoder.weight"]
+    batch = synth.pretrain_batch(B=3, L=24, seed=5)
+    with torch.no_grad():
+        scores, mlm_loss = PO.forward_mlm(P, batch)
+        gl, ll, fl, sap_loss = PO.forward_sap(P, batch)
+        go, vo, fo, to, cfp_loss = PO.forward_cfp(P, batch)
+
+    def rel(a, b):
+        fin = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), fin)
+        return (a[fin] - b[fin]).abs().max().item() / max(1.0, b[fin].abs().max().item())
+    assert rel(scores[:, :64], g["mlm_scores_head"]) < TOL and rel(mlm_loss, g["mlm_loss"]) < TOL
+    for a, k in ((gl, "sap_global_logits"), (ll, "sap_local_logits"), (fl, "sap_fused_logits"), (sap_loss, "sap_loss")):
+        assert rel(a, g[k]) < TOL, k
+    for a, k in ((go, "cfp_gmap"), (vo, "cfp_vp"), (fo, "cfp_fused"), (to, "cfp_txt"), (cfp_loss, "cfp_loss")):
+        assert rel(a, g[k]) < TOL, k
+
+
+def pretrain_state_shapes():
+    """{state_dict key: shape} of the full pretraining model, from the product module's own parameter containers (the
+    key list is checked against the reference's in tests/test_host_logic.py)."""
+    from vln_goat_b200 import pretrain_model
+    from vln_goat_b200.config import GoatConfig
+    with torch.device("meta"):
+        m = pretrain_model.GlocalTextPathCMTPreTraining(GoatConfig(pretrain_tasks=("mlm", "sap", "cfp")))
+    return [(k, tuple(v.shape)) for k, v in m.state_dict().items()]

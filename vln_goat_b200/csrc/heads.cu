@@ -44,11 +44,18 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(POOL_THREADS)
 attn_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int mode,
-                     int N, int H, float* __restrict__ out, float* __restrict__ a_out, float* __restrict__ s_out) {
+                     int Nfull, int H, float* __restrict__ out, float* __restrict__ a_out, float* __restrict__ s_out,
+                     const int* __restrict__ n_valid) {
   __shared__ float sc[POOL_MAX_N];
   __shared__ float red[POOL_THREADS / 32];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* xb = x + (size_t)b * N * H;
+  const float* xb = x + (size_t)b * Nfull * H;
+  // only the first N tokens are pooled (N = the batch's own padded length when the buffers are padded further)
+  const int N = n_valid ? max(1, min(Nfull, *n_valid)) : Nfull;
+  for (int n = N + threadIdx.x; n < Nfull; n += POOL_THREADS) {
+    if (s_out) s_out[(size_t)b * Nfull + n] = 0.f;
+    a_out[(size_t)b * Nfull + n] = 0.f;
+  }
   const float bv = (mode == 0 && bias) ? bias[0] : 0.f;
   for (int n = warp; n < N; n += POOL_THREADS / 32) {
     float d = 0.f;
@@ -71,8 +78,8 @@ attn_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   for (int n = threadIdx.x; n < N; n += POOL_THREADS) {
     const float s = sc[n];
     const float a = __expf(s - m) * inv;
-    if (s_out) s_out[(size_t)b * N + n] = s;
-    a_out[(size_t)b * N + n] = a;
+    if (s_out) s_out[(size_t)b * Nfull + n] = s;
+    a_out[(size_t)b * Nfull + n] = a;
     sc[n] = a;
   }
   __syncthreads();
@@ -86,13 +93,16 @@ attn_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
 __global__ void __launch_bounds__(POOL_THREADS)
 attn_pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ a, const float* __restrict__ s, const float* __restrict__ out, int mode,
-                     int N, int H, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+                     int Nfull, int H, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                     const int* __restrict__ n_valid) {
   __shared__ float dpre[POOL_MAX_H];
   __shared__ float coef[POOL_MAX_N];   // da_n, then ds_n (mode 1) / du_n (mode 0)
   __shared__ float red[POOL_THREADS / 32];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* xb = x + (size_t)b * N * H;
-  const float* ab = a + (size_t)b * N;
+  const float* xb = x + (size_t)b * Nfull * H;
+  const float* ab = a + (size_t)b * Nfull;
+  const int N = n_valid ? max(1, min(Nfull, *n_valid)) : Nfull;
+  for (int i = N * H + threadIdx.x; i < Nfull * H; i += POOL_THREADS) dx[(size_t)b * Nfull * H + i] = 0.f;
   for (int h = threadIdx.x; h < H; h += POOL_THREADS) {
     float g = dout[(size_t)b * H + h];
     if (mode == 1) {
@@ -117,7 +127,7 @@ attn_pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x
   for (int n = threadIdx.x; n < N; n += POOL_THREADS) {
     float ds = ab[n] * (coef[n] - c);
     if (mode == 0) {
-      const float sv = s[(size_t)b * N + n];
+      const float sv = s[(size_t)b * Nfull + n];
       ds *= 1.f - sv * sv;
       dbl += ds;
     }
@@ -142,7 +152,7 @@ attn_pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x
         d = fmaf(coef[n] * wh, 1.f - t * t, d);
         dwh = fmaf(coef[n], t, dwh);
       }
-      dx[((size_t)b * N + n) * H + h] = d;
+      dx[((size_t)b * Nfull + n) * H + h] = d;
     }
     if (dw) atomicAdd(dw + h, dwh);
   }
@@ -261,7 +271,8 @@ xent_fwd_kernel(const float* __restrict__ logits, long long sr, long long sc, co
     const float e = m + __logf(l);
     lse[i] = e;
     const long long lab = labels[i];
-    loss[i] = (lab == ignore_index) ? 0.f : e - row[(size_t)lab * sc];
+    // a label outside [0, N) that is not ignore_index is a caller bug (torch raises): no out-of-bounds read, NaN loss
+    loss[i] = (lab == ignore_index) ? 0.f : ((lab < 0 || lab >= N) ? CUDART_NAN_F : e - row[(size_t)lab * sc]);
   }
 }
 
@@ -271,7 +282,7 @@ xent_bwd_kernel(const float* __restrict__ dloss, const float* __restrict__ logit
                 float* __restrict__ dlogits, long long dsr, long long dsc, int accumulate) {
   const int i = blockIdx.x;
   const long long lab = labels[i];
-  const float g = (lab == ignore_index) ? 0.f : dloss[i];
+  const float g = (lab == ignore_index || lab < 0 || lab >= N) ? 0.f : dloss[i];
   const float e = lse[i];
   const float* row = logits + (size_t)i * sr;
   float* drow = dlogits + (size_t)i * dsr;
@@ -344,6 +355,56 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dout, const long long
   if (dtype) atomicAdd(dtype + h, g);
 }
 
+// ---------------------------------------------------------------------------------------------
+// out = dy * act'(ref) in one pass (heads / poolers); sprel_linear (1 -> 1) forward and its two scalar gradients
+// ---------------------------------------------------------------------------------------------
+template <typename R, typename Dt>
+__global__ void act_grad_kernel(const float* __restrict__ dy, const R* __restrict__ ref, int act, Dt* __restrict__ out,
+                                long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = dy[i];
+    if (act == GOAT_ACT_RELU) g = to_f<R>(ref[i]) > 0.f ? g : 0.f;
+    else if (act == GOAT_ACT_TANH) { const float y = to_f<R>(ref[i]); g *= 1.f - y * y; }
+    else if (act == GOAT_ACT_GELU) g *= dgelu_erf(to_f<R>(ref[i]));
+    out[i] = from_f<Dt>(g);
+  }
+}
+
+template <typename R>
+int act_grad_launch(const float* dy, const void* ref, int act, void* out, int od, long long n, cudaStream_t st) {
+  long long want = (n + 255) / 256;
+  const int grid = (int)(want > 148 * 8 ? 148 * 8 : want);
+  if (od == GOAT_F32) act_grad_kernel<R, float><<<grid, 256, 0, st>>>(dy, (const R*)ref, act, (float*)out, n);
+  else if (od == GOAT_F16) act_grad_kernel<R, __half><<<grid, 256, 0, st>>>(dy, (const R*)ref, act, (__half*)out, n);
+  else act_grad_kernel<R, __nv_bfloat16><<<grid, 256, 0, st>>>(dy, (const R*)ref, act, (__nv_bfloat16*)out, n);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+__global__ void sprel_fwd_kernel(const float* __restrict__ d, const float* __restrict__ w, const float* __restrict__ b,
+                                 float* __restrict__ out, long long n) {
+  const float ww = w[0], bb = b[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = fmaf(d[i], ww, bb);
+}
+__global__ void __launch_bounds__(256)
+sprel_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ d, float* __restrict__ dw, float* __restrict__ db,
+                 long long n) {
+  __shared__ float red[8];
+  float sw = 0.f, sb = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = dout[i];
+    sw = fmaf(g, d[i], sw);
+    sb += g;
+  }
+  sw = block_sum(sw, red);
+  sb = block_sum(sb, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(dw, sw);
+    atomicAdd(db, sb);
+  }
+}
+
 }  // namespace
 }  // namespace goat
 
@@ -352,26 +413,28 @@ using namespace goat;
 extern "C" {
 
 int goat_attn_pool_fwd(const float* x, const float* w, const float* bias, int mode, int B, int N, int H, float* out,
-                       float* a, float* s, goat_stream_t stream) {
+                       float* a, float* s, const int* n_valid, goat_stream_t stream) {
   GOAT_CHECK(x && w && out && a, "goat_attn_pool_fwd: null argument");
   GOAT_CHECK(mode == 0 || mode == 1, "goat_attn_pool_fwd: mode must be 0 (pano fusion) or 1 (CFP pooling)");
   GOAT_CHECK(mode == 1 || s, "goat_attn_pool_fwd: mode 0 needs the score buffer s");
   GOAT_CHECK(N >= 1 && N <= POOL_MAX_N && H >= 1 && H <= POOL_MAX_H, "goat_attn_pool_fwd: N=%d / H=%d out of range", N, H);
   if (B <= 0) return GOAT_OK;
-  attn_pool_fwd_kernel<<<B, POOL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, bias, mode, N, H, out, a, s);
+  attn_pool_fwd_kernel<<<B, POOL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, bias, mode, N, H, out, a, s,
+                                                                                      n_valid);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
 
 int goat_attn_pool_bwd(const float* dout, const float* x, const float* w, const float* a, const float* s, const float* out,
-                       int mode, int B, int N, int H, float* dx, float* dw, float* db, goat_stream_t stream) {
+                       int mode, int B, int N, int H, float* dx, float* dw, float* db, const int* n_valid,
+                       goat_stream_t stream) {
   GOAT_CHECK(dout && x && w && a && dx, "goat_attn_pool_bwd: null argument");
   GOAT_CHECK(mode == 0 || mode == 1, "goat_attn_pool_bwd: bad mode");
   GOAT_CHECK(mode == 0 ? s != nullptr : out != nullptr, "goat_attn_pool_bwd: mode 0 needs s, mode 1 needs out");
   GOAT_CHECK(N >= 1 && N <= POOL_MAX_N && H >= 1 && H <= POOL_MAX_H, "goat_attn_pool_bwd: N=%d / H=%d out of range", N, H);
   if (B <= 0) return GOAT_OK;
   attn_pool_bwd_kernel<<<B, POOL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, x, w, a, s, out, mode, N, H,
-                                                                                      dx, dw, db);
+                                                                                      dx, dw, db, n_valid);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
@@ -488,6 +551,39 @@ int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H,
   GOAT_CHECK(M <= 65535, "goat_embed_bwd: too many tokens per call (max 65535)");
   embed_bwd_kernel<<<dim3((H + 127) / 128, M), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, ids, L, H,
                                                                                                 padding_idx, dword, dpos, dtype);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+int goat_act_grad(const float* dy, const void* ref, int ref_dtype, int act, void* out, int out_dtype, long long n,
+                  goat_stream_t stream) {
+  GOAT_CHECK(dy && out, "goat_act_grad: null argument");
+  GOAT_CHECK(act == GOAT_ACT_NONE || ref, "goat_act_grad: the activation needs its reference tensor");
+  GOAT_CHECK(act == GOAT_ACT_NONE || act == GOAT_ACT_RELU || act == GOAT_ACT_TANH || act == GOAT_ACT_GELU,
+             "goat_act_grad: bad act %d", act);
+  GOAT_CHECK(out_dtype == GOAT_F32 || out_dtype == GOAT_F16 || out_dtype == GOAT_BF16, "goat_act_grad: bad out dtype");
+  if (n <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (act == GOAT_ACT_NONE || ref_dtype == GOAT_F32) return act_grad_launch<float>(dy, ref ? ref : dy, act, out, out_dtype, n, st);
+  if (ref_dtype == GOAT_F16) return act_grad_launch<__half>(dy, ref, act, out, out_dtype, n, st);
+  if (ref_dtype == GOAT_BF16) return act_grad_launch<__nv_bfloat16>(dy, ref, act, out, out_dtype, n, st);
+  GOAT_CHECK(false, "goat_act_grad: bad ref dtype");
+}
+
+int goat_sprel_fwd(const float* d, const float* w, const float* b, float* out, long long n, goat_stream_t stream) {
+  GOAT_CHECK(d && w && b && out, "goat_sprel_fwd: null argument");
+  if (n <= 0) return GOAT_OK;
+  long long want = (n + 255) / 256;
+  sprel_fwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d, w, b, out, n);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+int goat_sprel_bwd(const float* dout, const float* d, float* dw, float* db, long long n, goat_stream_t stream) {
+  GOAT_CHECK(dout && d && dw && db, "goat_sprel_bwd: null argument");
+  if (n <= 0) return GOAT_OK;
+  long long want = (n + 256 * 8 - 1) / (256 * 8);
+  sprel_bwd_kernel<<<(int)(want > 148 ? 148 : want), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, d, dw, db, n);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

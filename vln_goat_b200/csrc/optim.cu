@@ -40,18 +40,26 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(const float* __restr
 
 // hp (device, fp32): [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] 1-beta1^t  [6] 1-beta2^t
 //                    [7] max_grad_norm (<= 0: no clipping)  [8] gradient pre-scale (1/world for summed grads)
+// scaler (device, fp32, optional): the dynamic loss scale of the fp16 path (torch.cuda.amp.GradScaler semantics,
+//   P/train_r2r_goat.py:279,325,351-363): [0] scale  [1] clean steps since the last change  [2] 1 if the last step
+//   overflowed  [3] skipped steps so far  [4] optimizer steps actually taken.  With a scaler the gradients are divided
+//   by scaler[0] on top of hp[8], a non-finite gradient norm SKIPS the update (p, m, v, shadow untouched; the gradient
+//   buffer is still cleared), and the bias corrections are computed here from scaler[4] + 1 instead of hp[5], hp[6]
+//   (a skipped step does not advance Adam's step count).  goat_scaler_update() then moves the scale.
 template <typename TS>
 __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              TS* __restrict__ shadow, long long n, long long n_decay, const float* __restrict__ hp,
-             const float* __restrict__ partial, int nparts, float* __restrict__ norm_out, int zero_grad) {
+             const float* __restrict__ partial, int nparts, float* __restrict__ norm_out, int zero_grad,
+             const float* __restrict__ scaler) {
   __shared__ float s_coef;
+  __shared__ int s_skip;
   if (threadIdx.x < 32) {
     float t = 0.f;
     for (int i = threadIdx.x; i < nparts; i += 32) t += partial[i];
     t = warp_sum(t);
     if (threadIdx.x == 0) {
-      const float pre = hp[8];
+      const float pre = scaler ? hp[8] / scaler[0] : hp[8];
       const float norm = sqrtf(t) * pre;
       float coef = pre;
       if (hp[7] > 0.f) {
@@ -59,14 +67,30 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
         if (c < 1.f) coef *= c;
       }
       s_coef = coef;
+      s_skip = (scaler && !isfinite(t)) ? 1 : 0;
       if (blockIdx.x == 0 && norm_out) *norm_out = norm;
     }
   }
   __syncthreads();
   const float coef = s_coef;
-  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4];
-  const float step_size = lr * sqrtf(hp[6]) / hp[5];
   const long long n4 = n >> 2;
+  if (s_skip) {   // overflowed fp16 gradients: drop them, change nothing else
+    if (zero_grad) {
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (blockIdx.x == 0)
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) g[i] = 0.f;
+    }
+    return;
+  }
+  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4];
+  float bc1 = hp[5], bc2 = hp[6];
+  if (scaler && hp[5] != 1.0f) {   // hp[5] == 1 exactly: correct_bias off
+    const float t = scaler[4] + 1.0f;
+    bc1 = 1.0f - powf(b1, t);
+    bc2 = 1.0f - powf(b2, t);
+  }
+  const float step_size = lr * sqrtf(bc2) / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
@@ -109,6 +133,27 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
   }
 }
 
+// one thread: GradScaler.update() -- halve the scale after an overflow, double it after `interval` clean steps
+__global__ void scaler_update_kernel(float* __restrict__ scaler, const float* __restrict__ partial, int nparts, float growth,
+                                     float backoff, float interval) {
+  float t = 0.f;
+  for (int i = 0; i < nparts; ++i) t += partial[i];
+  if (!isfinite(t)) {
+    scaler[0] = fmaxf(scaler[0] * backoff, 1.0f);
+    scaler[1] = 0.f;
+    scaler[2] = 1.f;
+    scaler[3] += 1.f;
+  } else {
+    scaler[2] = 0.f;
+    scaler[4] += 1.f;
+    scaler[1] += 1.f;
+    if (scaler[1] >= interval) {
+      scaler[0] = fminf(scaler[0] * growth, 16777216.0f);
+      scaler[1] = 0.f;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace goat
 
@@ -129,7 +174,7 @@ extern "C" int goat_sumsq(const float* g, long long n, float* partial, int* npar
 
 extern "C" int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
                                long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
-                               int zero_grad, goat_stream_t stream) {
+                               int zero_grad, const float* scaler, goat_stream_t stream) {
   GOAT_CHECK(p && g && m && v && hp && partial, "goat_adamw_step: null argument");
   GOAT_CHECK(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || aligned16(shadow)),
              "goat_adamw_step: buffers must be 16-byte aligned");
@@ -140,11 +185,22 @@ extern "C" int goat_adamw_step(float* p, float* g, float* m, float* v, void* sha
   long long want = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   const int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
   if (shadow && shadow_dtype == GOAT_F16)
-    adamw_kernel<__half><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__half*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad);
+    adamw_kernel<__half><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__half*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler);
   else if (shadow)
-    adamw_kernel<__nv_bfloat16><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad);
+    adamw_kernel<__nv_bfloat16><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler);
   else
-    adamw_kernel<float><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (float*)nullptr, n, n_decay, hp, partial, nparts, norm_out, zero_grad);
+    adamw_kernel<float><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (float*)nullptr, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" int goat_scaler_update(float* scaler, const float* partial, int nparts, float growth, float backoff,
+                                  int interval, goat_stream_t stream) {
+  GOAT_CHECK(scaler && partial, "goat_scaler_update: null argument");
+  GOAT_CHECK(nparts >= 1 && nparts <= SUMSQ_MAX_PARTS, "goat_scaler_update: bad nparts");
+  GOAT_CHECK(growth >= 1.f && backoff > 0.f && backoff <= 1.f && interval >= 1, "goat_scaler_update: bad schedule");
+  scaler_update_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scaler, partial, nparts, growth, backoff,
+                                                                            (float)interval);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

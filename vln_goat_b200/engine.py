@@ -28,6 +28,17 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def _p_or_none(t):
+    return None if t is None else t.data_ptr()
+
+
+def _fold_autograd_grad(p):
+    if p.grad is not None:
+        p._goat_grad.add_(p.grad.to(torch.float32).view_as(p._goat_grad))
+        p.grad = None
+        p._goat_fresh = False
+
+
 class FlatParams(object):
     """Re-homes every trainable parameter of ``model`` (already on its CUDA device) into one flat fp32 buffer.
 
@@ -41,7 +52,13 @@ class FlatParams(object):
         model is left untouched and never updated -- the reference's AdamW likewise skips parameters whose
         ``grad`` is None (P/optim/adamw.py:66-67), which DDP's find_unused_parameters=True relies on.
         ``group``: the data-parallel process group (default: the world); the buffers are padded so that they split
-        into equal 16-byte aligned shards, one per rank (``sharded_step``)."""
+        into equal 16-byte aligned shards, one per rank (``sharded_step``).
+
+        Layout: [decayed matrices the GEMMs read through the 16-bit shadow | decayed tensors the kernels read in fp32
+        (embedding tables, LayerNorm gains not called ``LayerNorm``, pooling / gate vectors, 7- and 14-wide position
+        projections) | no-decay vectors (biases, ``LayerNorm.*``)].  ``n_decay`` ends the second region (weight decay);
+        ``n_shadow_only`` ends the first: everything after it must be current in FP32 on every rank after a sharded
+        optimizer step, everything before it only in the shadow."""
         named = []
         seen = set()
         keep = None if only is None else set(id(p) for p in only)
@@ -54,19 +71,28 @@ class FlatParams(object):
         dev = named[0][1].device
         if dev.type != "cuda":
             raise RuntimeError("FlatParams needs the model on a CUDA device (no CPU path)")
-        decay = [(n, p) for n, p in named if not any(nd in n for nd in no_decay)]
-        nodecay = [(n, p) for n, p in named if any(nd in n for nd in no_decay)]
+        emb = set(id(m.weight) for m in model.modules() if isinstance(m, torch.nn.Embedding))
+
+        def fp32_read(p):
+            # what functional.LinearFn / EmbedFn / the head kernels read straight from the fp32 master
+            return (id(p) in emb or p.dim() != 2 or p.shape[1] % 8 != 0 or p.shape[1] < 16 or p.shape[0] < 8)
+        is_nd = lambda n: any(nd in n for nd in no_decay)
+        decay_w = [(n, p) for n, p in named if not is_nd(n) and not fp32_read(p)]
+        decay_f = [(n, p) for n, p in named if not is_nd(n) and fp32_read(p)]
+        nodecay = [(n, p) for n, p in named if is_nd(n)]
         self.names, self.params, self.offsets = [], [], []
         off = 0
-        for n, p in decay + nodecay:
-            self.names.append(n)
-            self.params.append(p)
-            self.offsets.append(off)
-            off += _pad8(p.numel())
-            if len(self.params) == len(decay):
+        self.n_shadow_only = self.n_decay = 0
+        for gi, grp in enumerate((decay_w, decay_f, nodecay)):
+            for n, p in grp:
+                self.names.append(n)
+                self.params.append(p)
+                self.offsets.append(off)
+                off += _pad8(p.numel())
+            if gi == 0:
+                self.n_shadow_only = off
+            if gi == 1:
                 self.n_decay = off
-        if not decay:
-            self.n_decay = 0
         from .dist_utils import world_size
         self.group = group
         self.world = world_size(group)
@@ -82,6 +108,9 @@ class FlatParams(object):
         self.shadow = torch.zeros(tot, device=dev, dtype=self.shadow_dtype) if self.shadow_dtype else None
         self._g_shard = self._x_shard = None
         self.master_synced = True
+        self.scaler = None
+        self._scaler_cfg = None
+        self._hooks = []
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             self.p[o:o + n].copy_(p.detach().reshape(-1))
@@ -91,6 +120,10 @@ class FlatParams(object):
             p._goat_fresh = True
             if self.shadow is not None:
                 p._goat_shadow = self.shadow[o:o + n].view(p.shape)
+            # a parameter that some torch-native op consumed gets its gradient through autograd: fold it into the flat
+            # buffer as soon as it is accumulated (nothing on the GOAT path should need this; it keeps foreign ops
+            # correct instead of silently untrained)
+            self._hooks.append(p.register_post_accumulate_grad_hook(_fold_autograd_grad))
         self.refresh_shadow()
         ws = _lib.lib().goat_sumsq_workspace_bytes()
         self._partial = torch.zeros(ws // 4, device=dev, dtype=torch.float32)
@@ -98,17 +131,47 @@ class FlatParams(object):
         self._hp = torch.zeros(9, device=dev, dtype=torch.float32)
         self.step_count = 0
 
+    # ------------------------------------------------------------------------------------------
+    # fp16 loss scaling (torch.cuda.amp.GradScaler of the reference's 16-bit path, P/train_r2r_goat.py:279,325,351-363)
+    # ------------------------------------------------------------------------------------------
+    def enable_loss_scale(self, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        """Dynamic loss scale held ON THE DEVICE (``scaler``: [scale, clean steps, overflowed, skipped, steps taken]):
+        multiply the loss by ``loss_scale()`` before backward; the optimizer kernel unscales, skips the update when the
+        gradient norm is not finite, and ``goat_scaler_update`` moves the scale -- no host synchronisation, so the
+        scaled backward can sit inside a replayed CUDA graph."""
+        self.scaler = torch.tensor([init_scale, 0.0, 0.0, 0.0, 0.0], device=self.p.device, dtype=torch.float32)
+        self._scaler_cfg = (float(growth_factor), float(backoff_factor), int(growth_interval))
+        return self.scaler
+
+    def loss_scale(self):
+        """device scalar (a view of the scaler state) to multiply the loss with, or None when scaling is off"""
+        return None if self.scaler is None else self.scaler[0]
+
+    def _scaler_update(self, nparts, st):
+        if self.scaler is not None:
+            g, b, i = self._scaler_cfg
+            _lib.check(_lib.lib().goat_scaler_update(self.scaler.data_ptr(), self._partial.data_ptr(), nparts, g, b, i, st),
+                       "goat_scaler_update")
+            ops.LAUNCHES[0] += 1
+
     def refresh_shadow(self):
         """Re-derive the 16-bit operand copies from the fp32 masters (after load_state_dict etc.)."""
+        from . import runtime
         if self.shadow is not None:
             ops.cast(self.p, self.shadow_dtype, out=self.shadow)
+        runtime.bump_generation()
 
     def begin_step(self):
-        """Mark every gradient view as unwritten.  Vector gradients (biases, LayerNorm) overwrite on their first
-        write of a step and add afterwards; weight gradients always accumulate (split-K atomics) into the buffer
-        that ``adamw_step`` left zeroed."""
+        """Reset the written-this-step diagnostic (``unwritten()``).  It does NOT touch the gradients: every backward
+        ACCUMULATES into the flat gradient buffer (functional._grad_into), the optimizer step clears it; call
+        ``zero_grad()`` to drop gradients without stepping.  Several backward passes between two optimizer steps sum,
+        like ``.grad`` under the reference's gradient_accumulation_steps (P/train_r2r_goat.py:322-327)."""
         for p in self.params:
             p._goat_fresh = True
+
+    def zero_grad(self):
+        self.g.zero_()
+        self.begin_step()
 
     def unwritten(self):
         return [n for n, p in zip(self.names, self.params) if p._goat_fresh]
@@ -142,7 +205,8 @@ class FlatParams(object):
     def sharded_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, correct_bias=True):
         """One data-parallel optimizer step with the optimizer state's work split over the ranks (see above).
         Afterwards every rank holds the new 16-bit operand shadow and the new fp32 no-decay vectors (biases,
-        LayerNorm); the fp32 master WEIGHTS are current only on their owner rank until ``sync_master()``
+        LayerNorm, embedding tables, every tensor past ``n_shadow_only``); the fp32 master MATRICES that are only ever
+        read through the shadow are current only on their owner rank until ``sync_master()``
         (call it before ``state_dict()`` / checkpointing).  Without a 16-bit shadow (fp32 compute) the whole fp32
         buffer is all-gathered every step instead."""
         import torch.distributed as dist
@@ -170,18 +234,22 @@ class FlatParams(object):
                                      self.v[lo:lo + S].data_ptr(),
                                      self.shadow[lo:lo + S].data_ptr() if self.shadow is not None else None, sd, S,
                                      n_decay_local, self._hp.data_ptr(), self._partial.data_ptr(), 1,
-                                     self.grad_norm.data_ptr(), 0, st), "goat_adamw_step")
+                                     self.grad_norm.data_ptr(), 0, _p_or_none(self.scaler), st), "goat_adamw_step")
         ops.LAUNCHES[0] += 2
+        self._scaler_update(1, st)
         if self.shadow is not None:
             self._x_shard.copy_(self.shadow[lo:lo + S])
             D.all_gather_flat(self.shadow, self._x_shard, self.group)
-            # fp32 vectors the kernels read directly (biases, LayerNorm): broadcast each owner's piece of the no-decay tail
-            for r, a, b in D.tail_pieces(self.n_decay, self.numel, S, W):
+            # everything the kernels read in FP32 (embedding tables, LayerNorm gains, pooling / gate vectors, biases):
+            # each owner broadcasts its piece of [n_shadow_only, numel)
+            for r, a, b in D.tail_pieces(self.n_shadow_only, self.numel, S, W):
                 dist.broadcast(self.p[a:b], src=D.group_src(r, self.group), group=self.group)
             self.master_synced = False
         else:
             self._x_shard.copy_(self.p[lo:lo + S])
             D.all_gather_flat(self.p, self._x_shard, self.group)
+        from . import runtime
+        runtime.bump_generation()
 
     def sync_master(self):
         """All-gather the fp32 master weights after sharded steps (every rank then holds the full, identical fp32
@@ -206,8 +274,11 @@ class FlatParams(object):
         _lib.check(L.goat_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                      self.shadow.data_ptr() if self.shadow is not None else None, sd, self.numel,
                                      self.n_decay, self._hp.data_ptr(), self._partial.data_ptr(), nparts.value,
-                                     self.grad_norm.data_ptr(), 1, st), "goat_adamw_step")
+                                     self.grad_norm.data_ptr(), 1, _p_or_none(self.scaler), st), "goat_adamw_step")
         ops.LAUNCHES[0] += 2
+        self._scaler_update(nparts.value, st)
+        from . import runtime
+        runtime.bump_generation()
 
 
 def active_parameters(model, loss_fn, inputs):
@@ -232,72 +303,147 @@ def warmup_linear(step, warmup_step, tot_step):
     return max(0, (tot_step - step) / (tot_step - warmup_step))
 
 
-class TrainStep(object):
-    """One optimizer step = forward + backward (captured in a CUDA graph) + gradient all-reduce + fused AdamW.
+def _map_inputs(inputs, fn):
+    if isinstance(inputs, dict):
+        return {k: fn(v) for k, v in inputs.items()}
+    return [fn(v) for v in inputs]
 
-    ``loss_fn(*static_inputs) -> scalar loss tensor`` must be shape-static; call ``step(*new_inputs)`` with
-    tensors of the same shapes (device or pinned-host; they are copied into the captured input buffers).
+
+def _input_items(inputs):
+    return list(inputs.items()) if isinstance(inputs, dict) else list(enumerate(inputs))
+
+
+def input_signature(inputs):
+    """Shape / dtype signature of a set of step inputs: the key of the captured-graph cache."""
+    return tuple((k, tuple(v.shape), str(v.dtype)) for k, v in _input_items(inputs))
+
+
+class _Captured(object):
+    """forward + backward of one (loss_fn, input signature) pair, captured in a CUDA graph over static input buffers"""
+    __slots__ = ("loss_fn", "static_inputs", "graph", "loss", "launches")
+
+
+class TrainStep(object):
+    """One optimizer step = forward + backward (captured in a CUDA graph) + gradient exchange + fused AdamW.
+
+    ``loss_fn(*static_inputs)`` (list inputs) or ``loss_fn(static_inputs)`` (dict inputs) -> scalar loss tensor; it must
+    be shape-static.  ``step(new_inputs)`` takes tensors of the same shapes (device or pinned host; they are copied into
+    the captured input buffers).  Several (loss_fn, shapes) pairs can share one TrainStep -- the pretraining loop
+    alternates MLM / SAP / CFP batches whose padded shapes fall into a few buckets (P/train_r2r_goat.py:301-314):
+    ``capture(key, loss_fn, example_inputs)`` adds a graph, ``step(inputs, key)`` replays it.
     """
 
-    def __init__(self, flat, loss_fn, example_inputs, lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01,
-                 max_grad_norm=5.0, use_graph=True, warmup_iters=2, shard_optimizer=True):
+    SEED_STRIDE = 16     # a block uses host seeds seed .. seed+3 for its dropout sites: advance past all of them per step
+
+    def __init__(self, flat, loss_fn=None, example_inputs=None, lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01,
+                 max_grad_norm=5.0, use_graph=True, warmup_iters=2, shard_optimizer=True, check_unwritten=True):
         """``shard_optimizer``: at world size > 1 use FlatParams.sharded_step (reduce-scatter, 1/world of the AdamW
-        pass per rank, all-gather of the operand shadow) instead of all-reduce + a full AdamW pass on every rank."""
-        self.flat, self.loss_fn = flat, loss_fn
+        pass per rank, all-gather of the operand shadow) instead of all-reduce + a full AdamW pass on every rank.
+        If ``flat.enable_loss_scale()`` was called, the loss is multiplied by the device-resident scale before
+        backward and the optimizer kernel unscales / skips on overflow."""
+        self.flat = flat
         self.shard_optimizer = shard_optimizer
+        self.use_graph = use_graph
+        self.warmup_iters = warmup_iters
+        self.check_unwritten = check_unwritten
         self.opt = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
-        self.static_inputs = [t.clone() if t.is_cuda else t.cuda() for t in example_inputs]
-        dev = self.static_inputs[0].device
+        dev = flat.p.device
         self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
         Fn.set_seed_ptr(self.seed)
+        self.entries = {}
         self.loss = None
-        self.graph = None
         self.launches_per_step = None
+        if loss_fn is not None:
+            self.capture(None, loss_fn, example_inputs)
+
+    # compatibility with the single-graph form
+    @property
+    def static_inputs(self):
+        return self.entries[None].static_inputs
+
+    @property
+    def graph(self):
+        return self.entries[None].graph
+
+    def has(self, key):
+        return key in self.entries
+
+    def capture(self, key, loss_fn, example_inputs):
+        from . import runtime
+        flat = self.flat
+        e = _Captured()
+        e.loss_fn = loss_fn
+        dev = flat.p.device
+        e.static_inputs = _map_inputs(example_inputs, lambda t: t.clone() if t.is_cuda else t.to(dev))
+        e.graph = None
+        e.loss = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup_iters):
-                self._fwd_bwd()
+            for _ in range(self.warmup_iters):
+                self._fwd_bwd(e)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        missing = flat.unwritten()
-        if missing:
-            raise RuntimeError("parameters without a gradient in the captured step (stale flat grads): %s" % missing[:8])
+        if self.check_unwritten:
+            missing = flat.unwritten()
+            if missing:
+                raise RuntimeError("parameters without a gradient in the captured step: %s" % missing[:8])
+        # operand casts made by the warm-up passes must not be reused by the capture (they would be baked in as
+        # constants); a new generation makes every cast part of the graph
+        runtime.bump_generation()
         n0 = ops.LAUNCHES[0]
-        if use_graph:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._fwd_bwd()
+        if self.use_graph:
+            e.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(e.graph):
+                self._fwd_bwd(e)
         else:
-            self._fwd_bwd()
-        self.launches_per_step = ops.LAUNCHES[0] - n0 + 2  # + sumsq + adamw
+            self._fwd_bwd(e)
+        e.launches = ops.LAUNCHES[0] - n0 + 2 + (1 if flat.scaler is not None else 0)  # + sumsq + adamw (+ scaler)
+        self.launches_per_step = e.launches
         torch.cuda.synchronize()
-        flat.g.zero_()   # drop what the warm-up / capture passes accumulated
+        flat.zero_grad()   # drop what the warm-up / capture passes accumulated
+        self.entries[key] = e
+        return e
 
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, e):
         self.flat.begin_step()
-        loss = self.loss_fn(*self.static_inputs)
-        loss.backward()
-        self.seed.add_(1)
-        self.loss = loss.detach()
-
-    def load_inputs(self, inputs):
-        for dst, src in zip(self.static_inputs, inputs):
-            dst.copy_(src, non_blocking=True)
-
-    def step(self, inputs=None):
-        if inputs is not None:
-            self.load_inputs(inputs)
-        if self.graph is not None:
-            self.graph.replay()
+        if isinstance(e.static_inputs, dict):
+            loss = e.loss_fn(e.static_inputs)
         else:
-            self._fwd_bwd()
+            loss = e.loss_fn(*e.static_inputs)
+        scale = self.flat.loss_scale()
+        (loss if scale is None else loss * scale).backward()
+        self.seed.add_(self.SEED_STRIDE)
+        e.loss = loss.detach()
+
+    def load_inputs(self, inputs, key=None):
+        e = self.entries[key]
+        if isinstance(e.static_inputs, dict):
+            for k, dst in e.static_inputs.items():
+                dst.copy_(inputs[k], non_blocking=True)
+        else:
+            for dst, src in zip(e.static_inputs, inputs):
+                dst.copy_(src, non_blocking=True)
+
+    def step(self, inputs=None, key=None):
+        e = self.entries[key]
+        if inputs is not None:
+            self.load_inputs(inputs, key)
+        if e.graph is not None:
+            e.graph.replay()
+        else:
+            self._fwd_bwd(e)
+        self.launches_per_step = e.launches
+        self.optimizer_step()
+        self.loss = e.loss
+        return e.loss
+
+    def optimizer_step(self):
         if self.shard_optimizer and self.flat.world > 1:
             self.flat.sharded_step(**self.opt)
         else:
             world = self.flat.all_reduce(self.flat.group)
             self.flat.adamw_step(grad_scale=1.0 / world, **self.opt)
-        return self.loss
 
 
-__all__ = ["FlatParams", "TrainStep", "active_parameters", "warmup_linear", "NO_DECAY"]
+__all__ = ["FlatParams", "TrainStep", "active_parameters", "warmup_linear", "input_signature", "NO_DECAY"]

@@ -64,76 +64,59 @@ def _split_rows(t, params):
     return tuple(out)
 
 
-def _grad_into(params, fn, can_acc, always_acc=False):
+def _mark(params):
+    for p in params:
+        if p is not None:
+            p._goat_fresh = False      # diagnostic only (engine.FlatParams.unwritten)
+
+
+def _grad_into(params, fn, can_acc):
     """Produce the gradient of one parameter, or of several whose rows are concatenated (fused QKV).
 
-    ``fn(out, acc)`` computes it into ``out`` (allocating when None), adding to the existing contents when
-    ``acc``.  If the parameters live in an engine.FlatParams buffer the result is written straight into their
-    flat gradient views (first write of a step overwrites, later writes accumulate) and None is returned for
-    autograd; otherwise the tensors are returned for autograd to accumulate the usual way."""
+    ``fn(out)`` computes it; with ``out`` given it ADDS the result to ``out`` (a zero-initialised tensor is allocated
+    when None).  ONE policy for every parameter that lives in an engine.FlatParams buffer: gradients are ACCUMULATED
+    into the flat gradient views, which are zero at step start (the optimizer kernel clears them; FlatParams.zero_grad()
+    does it explicitly) -- several backward passes between two optimizer steps therefore sum, as torch's ``.grad``
+    does under gradient accumulation (P/train_r2r_goat.py:322-327).  None is returned for autograd in that case;
+    otherwise the tensors are returned for autograd to accumulate the usual way."""
     dsts = [getattr(p, "_goat_grad", None) for p in params]
     if all(d is not None for d in dsts):
         from . import runtime
-        fresh = [p._goat_fresh for p in params]
-        if len(dsts) == 1 or runtime._adjacent(dsts):
-            dst = dsts[0] if len(dsts) == 1 else runtime._fused_view(dsts)
-            if always_acc:
-                fn(dst, True)      # the flat gradient buffer is zero at step start (the optimizer kernel clears it)
-            elif all(fresh):
-                fn(dst, False)
-            elif not any(fresh) and can_acc:
-                fn(dst, True)
-            else:
-                t = fn(None, False)
-                for d, part, f in zip(dsts, _split_rows(t, params), fresh):
-                    d.copy_(part) if f else d.add_(part)
+        if can_acc and (len(dsts) == 1 or runtime._adjacent(dsts)) and dsts[0].is_contiguous():
+            fn(dsts[0] if len(dsts) == 1 else runtime._fused_view(dsts))
         else:
-            t = fn(None, False)
-            for d, part, f in zip(dsts, _split_rows(t, params), fresh):
-                d.copy_(part) if f else d.add_(part)
-        for p in params:
-            p._goat_fresh = False
+            t = fn(None)
+            for d, part in zip(dsts, _split_rows(t, params)):
+                d.add_(part)
+        _mark(params)
         return (None,) * len(params)
-    t = fn(None, False)
+    t = fn(None)
     return _split_rows(t, params) if len(params) > 1 else (t,)
 
 
 def _wgrad(params, dy_c, x_c):
     """dW = dY^T X for weight(s) [N,K] (rows of several weights concatenated)."""
-    def fn(out, acc):
-        # split-K + atomic accumulate: into the (optimizer-zeroed) flat gradient view, or into fresh zeros
-        return ops.gemm(dy_c, x_c, a_mn=True, b_mn=True, out=out, accumulate=True)
-    return _grad_into(params, fn, True, always_acc=True)
+    # split-K + atomic accumulate: into the flat gradient view, or into fresh zeros
+    return _grad_into(params, lambda out: ops.gemm(dy_c, x_c, a_mn=True, b_mn=True, out=out, accumulate=True), True)
 
 
 def _bgrad(params, dy_c):
     """db = column sums of dY."""
     if params[0] is None:
         return (None,) * len(params)
-    # one atomic-accumulate kernel straight into the (optimizer-zeroed) flat gradient view, or into fresh zeros
-    return _grad_into(params, lambda out, acc: ops.colsum(dy_c, out=out, accumulate=True), True, always_acc=True)
+    # one atomic-accumulate kernel straight into the flat gradient view, or into fresh zeros
+    return _grad_into(params, lambda out: ops.colsum(dy_c, out=out, accumulate=True), True)
 
 
 def _vgrad(param, t):
     """a gradient vector that a kernel already produced (LayerNorm dgamma/dbeta, LN-fused bias column sums)"""
     if param is None:
         return None
-    return _grad_into((param,), lambda out, acc: t if out is None else out.copy_(t), False)[0]
-
-
-def _vdst(param):
-    """flat-gradient destination for a vector gradient if it can simply be overwritten this step, else None"""
-    if param is None:
-        return None
-    d = getattr(param, "_goat_grad", None)
-    if d is None or not param._goat_fresh or not d.is_contiguous():
-        return None
-    param._goat_fresh = False
-    return d
+    return _grad_into((param,), lambda out: t, False)[0]
 
 
 def _adst(param):
-    """flat-gradient destination a kernel may ACCUMULATE into (the optimizer left the buffer zeroed), else None"""
+    """flat-gradient destination a kernel may ACCUMULATE into, else None"""
     if param is None:
         return None
     d = getattr(param, "_goat_grad", None)
@@ -151,17 +134,11 @@ def _ln_bwd(dy32, x, gamma, mean, rstd, dres, cdt16, p, seed, seed_ptr, gamma_p,
         dx32, dx16, _, _, _ = ops.layernorm_bwd(dy32, x, gamma, mean, rstd, dres, True, cdt16, p, seed, seed_ptr,
                                                 want_colsum=bias_p is not None, dgamma_out=ag, dbeta_out=ab,
                                                 dcol_out=ac, accumulate=True)
-        for q in (gamma_p, beta_p, bias_p):
-            if q is not None:
-                q._goat_fresh = False
+        _mark((gamma_p, beta_p, bias_p))
         return dx32, dx16, None, None, None
-    og, ob = _vdst(gamma_p), _vdst(beta_p)
-    oc = _vdst(bias_p)
     dx32, dx16, dg, db, dcol = ops.layernorm_bwd(dy32, x, gamma, mean, rstd, dres, True, cdt16, p, seed, seed_ptr,
-                                                 want_colsum=bias_p is not None, dgamma_out=og, dbeta_out=ob,
-                                                 dcol_out=oc)
-    return (dx32, dx16, None if og is not None else _vgrad(gamma_p, dg), None if ob is not None else _vgrad(beta_p, db),
-            None if (oc is not None or bias_p is None) else _vgrad(bias_p, dcol))
+                                                 want_colsum=bias_p is not None)
+    return dx32, dx16, _vgrad(gamma_p, dg), _vgrad(beta_p, db), None if bias_p is None else _vgrad(bias_p, dcol)
 
 
 def _ln_bwd_split(dy32, pre, gamma, mean, rstd, cdt, p, seed, seed_ptr, gamma_p, beta_p, bias_p):
@@ -458,14 +435,12 @@ class LinearFn(torch.autograd.Function):
         xc, W_c, y, aux = ctx.saved_tensors
         cdt = ctx.cdt
         dy = dy.contiguous()
-        if ctx.act == ops.ACT_RELU:
-            dy = dy * (y > 0).to(dy.dtype)
-        elif ctx.act == ops.ACT_TANH:
-            dy = dy * (1.0 - y * y)
+        if ctx.act in (ops.ACT_RELU, ops.ACT_TANH):
+            dyc = ops.act_grad(dy, y, ctx.act, cdt)          # dy * act'(y), converted to the operand dtype, one kernel
         elif ctx.act == ops.ACT_GELU:
-            a = aux.float()
-            dy = dy * (0.5 * (1.0 + torch.erf(a * 0.7071067811865476)) + a * torch.exp(-0.5 * a * a) * 0.3989422804014327)
-        dyc = dy if cdt == torch.float32 else ops.cast(dy, cdt)
+            dyc = ops.act_grad(dy, aux, ctx.act, cdt)
+        else:
+            dyc = dy if cdt == torch.float32 else ops.cast(dy, cdt)
         W, b = ctx.params
         db, = _bgrad((b,), dyc)
         dW, = _wgrad((W,), dyc, xc)
@@ -500,15 +475,13 @@ class LayerNormFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------
 def _acc_dst(param, shape=None):
     """Destination a kernel can ACCUMULATE a parameter gradient into: the parameter's flat-gradient view when it
-    lives in an engine.FlatParams buffer (cleared first if nothing has written it this step), else fresh zeros that
-    are handed back to autograd.  -> (tensor, returned_to_autograd)"""
+    lives in an engine.FlatParams buffer (zero at step start, see _grad_into), else fresh zeros that are handed back
+    to autograd.  -> (tensor, returned_to_autograd)"""
     if param is None:
         return None, False
     d = getattr(param, "_goat_grad", None)
     if d is not None and d.is_contiguous():
-        if param._goat_fresh:
-            d.zero_()
-            param._goat_fresh = False
+        param._goat_fresh = False
         return d, False
     return torch.zeros(param.shape if shape is None else shape, device=param.device, dtype=torch.float32), True
 
@@ -518,12 +491,14 @@ class AttnPoolFn(torch.autograd.Function):
     mode 1: out = tanh(sum_n softmax_n(tanh(x_n) . w) x_n)    (CFP pooling, P/model/pretrain_goat.py:502-515)"""
 
     @staticmethod
-    def forward(ctx, x, w, b, mode):
+    def forward(ctx, x, w, b, mode, n_valid=None):
+        """n_valid: optional CUDA int32 [1] -- pool over the first n_valid tokens only (see goat_attn_pool_fwd)"""
         x = x.contiguous()
         wv = w.detach().reshape(-1).contiguous()
-        out, a, s = ops.attn_pool_fwd(x, wv, None if b is None else b.detach().contiguous(), mode)
+        out, a, s = ops.attn_pool_fwd(x, wv, None if b is None else b.detach().contiguous(), mode, n_valid)
         ctx.mode = mode
         ctx.params = (w, b)
+        ctx.n_valid = n_valid
         ctx.save_for_backward(x, wv, a, s, out)
         return out
 
@@ -533,8 +508,9 @@ class AttnPoolFn(torch.autograd.Function):
         w, b = ctx.params
         dw, ret_w = _acc_dst(w)
         db, ret_b = _acc_dst(b)
-        dx = ops.attn_pool_bwd(dout.contiguous(), x, wv, a, s, out, ctx.mode, dw.view(-1), None if db is None else db.view(-1))
-        return dx, (dw if ret_w else None), (db if ret_b else None), None
+        dx = ops.attn_pool_bwd(dout.contiguous(), x, wv, a, s, out, ctx.mode, dw.view(-1), None if db is None else db.view(-1),
+                               ctx.n_valid)
+        return dx, (dw if ret_w else None), (db if ret_b else None), None, None
 
 
 class WSumFn(torch.autograd.Function):
@@ -639,6 +615,48 @@ class EmbedFn(torch.autograd.Function):
         dt_, rt = _acc_dst(type_) if need[3] else (None, False)
         ops.embed_bwd(dout.contiguous(), ids, dw, dp, None if dt_ is None else dt_[0], ctx.padding_idx)
         return None, (dw if rw else None), (dp if rp else None), (dt_ if rt else None), None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """table[ids]  (nn.Embedding of the global-map step ids, P/model/vilmodel_goat.py:478-480): one gather kernel; the
+    table gradient is accumulated into the flat gradient view (or returned to autograd)."""
+
+    @staticmethod
+    def forward(ctx, ids, table):
+        shp = ids.shape
+        idx = ids.reshape(-1, 1).to(torch.int32).contiguous()
+        ctx.params = (table,)
+        ctx.save_for_backward(idx)
+        return ops.segment_reduce_fwd(table.detach().contiguous(), idx, False).view(shp + (table.shape[1],))
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx, = ctx.saved_tensors
+        table, = ctx.params
+        dst, ret = _acc_dst(table)
+        ops.segment_reduce_bwd(dout.reshape(idx.shape[0], -1).contiguous(), idx, False, table.shape[0], out=dst)
+        return None, (dst if ret else None)
+
+
+class SprelFn(torch.autograd.Function):
+    """sprel_linear = nn.Linear(1, 1) over the pairwise distances: d * w + b  (P/model/vilmodel_goat.py:499-501).  The
+    distances are data; dw / db are two scalar reductions accumulated by one kernel."""
+
+    @staticmethod
+    def forward(ctx, d, w, b):
+        d = d.to(torch.float32).contiguous()
+        ctx.params = (w, b)
+        ctx.save_for_backward(d)
+        return ops.sprel_fwd(d, w.detach().reshape(1), b.detach().reshape(1))
+
+    @staticmethod
+    def backward(ctx, dout):
+        d, = ctx.saved_tensors
+        w, b = ctx.params
+        dw, rw = _acc_dst(w)
+        db, rb = _acc_dst(b)
+        ops.sprel_bwd(dout.contiguous(), d, dw.view(-1), db.view(-1))
+        return None, (dw if rw else None), (db if rb else None)
 
 
 class DropoutFn(torch.autograd.Function):

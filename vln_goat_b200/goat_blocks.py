@@ -150,9 +150,10 @@ def cross_entropy(logits, labels, ignore_index=-100):
     return Fn.XentFn.apply(logits, labels, ignore_index)
 
 
-def attn_pool_cfp(x, attn_vec):
-    """tanh(sum_n softmax_n(tanh(x_n) . a) x_n)   P/model/pretrain_goat.py:502-515"""
-    return Fn.AttnPoolFn.apply(x, attn_vec, None, 1)
+def attn_pool_cfp(x, attn_vec, n_valid=None):
+    """tanh(sum_n softmax_n(tanh(x_n) . a) x_n)   P/model/pretrain_goat.py:502-515
+    n_valid: CUDA int32 [1], pool over the first n_valid tokens only (statically padded buffers)"""
+    return Fn.AttnPoolFn.apply(x, attn_vec, None, 1, n_valid)
 
 
 def infonce(a, b, temperature):
@@ -360,7 +361,7 @@ class CausalImageEmbeddings(nn.Module):
             x = self.back_door(x, z_img_features, z_img_pzs)
         if loc_after_do:
             x = x + loc
-        img_masks = gen_seq_masks(view_lens)
+        img_masks = gen_seq_masks(view_lens, view_img_fts.shape[1])
         x = Fn.dropout(x, self.dropout.p, self.training)
         x = self.img_self_encoder.run(x, img_masks.logical_not()).tensor()
         fused = self.pano_fuse(x) if self.config.adaptive_pano_fusion else None
@@ -418,6 +419,18 @@ class LocalVPEncoder(nn.Module):
         vp_img = torch.cat([cur.new_zeros(B, 1, H), cur], 1)[:, :max_vp_len]    # [stop] token first
         return vp_img + _pos_embed(self.vp_pos_embeddings, vp_pos_fts), vp_masks
 
+    def vp_input_embedding_flat(self, views, view_lens, last_rows, vp_pos_fts):
+        """views [S,V,H], view_lens [S], last_rows int32 [B,1] (row of each sample's current panorama) -> the same
+        (vp_embeds [B,Nq,H], vp_masks [B,Nq]) with Nq = vp_pos_fts.shape[1], through one gather kernel."""
+        S, V, H = views.shape
+        B, Nq = vp_pos_fts.shape[0], vp_pos_fts.shape[1]
+        cur = Fn.SegmentReduceFn.apply(views.reshape(S, V * H), last_rows, False).view(B, V, H)
+        vp_lens = view_lens[last_rows.view(-1).long()] + 1
+        vp_img = torch.cat([cur.new_zeros(B, 1, H), cur], 1)[:, :Nq]            # [stop] token first
+        if vp_img.shape[1] < Nq:
+            vp_img = torch.cat([vp_img, cur.new_zeros(B, Nq - vp_img.shape[1], H)], 1)
+        return vp_img + _pos_embed(self.vp_pos_embeddings, vp_pos_fts), gen_seq_masks(vp_lens, Nq)
+
     def forward(self, txt_embeds, txt_masks, split_traj_embeds, split_traj_vp_lens, vp_pos_fts):
         vp_embeds, vp_masks = self.vp_input_embedding(split_traj_embeds, split_traj_vp_lens, vp_pos_fts)
         return self.encoder(vp_embeds, vp_masks, txt_embeds, txt_masks)
@@ -449,13 +462,33 @@ def build_gmap_index(traj_step_lens, view_lens, traj_vpids, traj_cand_vpids, gma
                     unvisited.setdefault(vp, []).append(S + s * num_views + j)
         off += n_steps
         rows.append([visited[vp] if vp in visited else unvisited[vp] for vp in gmap_vpids[i][start_id:]])
-    G = max(len(r) for r in rows)
-    K = max(1, max((len(e) for r in rows for e in r), default=1))
-    idx = torch.full((len(rows), G, K), -1, dtype=torch.int32)
+    return _pack_index(rows)
+
+
+def _pack_index(rows, G=None, K=None):
+    """list (batch) of lists (nodes) of index lists -> int32 [B, G, K] padded with -1, filled through ONE numpy array
+    (no per-node tensor construction)."""
+    import numpy as np
+    Gn = max(len(r) for r in rows)
+    Kn = max(1, max((len(e) for r in rows for e in r), default=1))
+    G = Gn if G is None else G
+    K = Kn if K is None else K
+    if Gn > G or Kn > K:
+        raise ValueError("index lists need [%d, %d] slots but only [%d, %d] were given" % (Gn, Kn, G, K))
+    arr = np.full((len(rows), G, K), -1, dtype=np.int32)
     for i, r in enumerate(rows):
         for g, e in enumerate(r):
-            idx[i, g, :len(e)] = torch.tensor(e, dtype=torch.int32)
-    return idx
+            if e:
+                arr[i, g, :len(e)] = e
+    return torch.from_numpy(arr)
+
+
+def split_gmap_index(idx, S):
+    """Index lists over cat([fused [S], views [S*V]]) -> (idx_fused over the S fused rows, idx_views over the S*V view
+    rows), each int32 with -1 for empty.  A node has entries in only one of the two."""
+    idx_f = torch.where(idx < S, idx, torch.full_like(idx, -1))[..., :1].contiguous()
+    idx_v = torch.where(idx >= S, idx - S, torch.full_like(idx, -1))
+    return idx_f, idx_v
 
 
 class GlobalMapEncoder(nn.Module):
@@ -472,39 +505,51 @@ class GlobalMapEncoder(nn.Module):
             self.tim_self_encoder = BertAttention(config)
         self.sprel_linear = nn.Linear(1, 1) if config.graph_sprels else None
 
+    def aggregate_flat(self, views, fused, idx_f, idx_v):
+        """views [S,V,H], fused [S,H] or None, idx_f int32 [B,G1,1] (rows of fused), idx_v int32 [B,G1,K] (rows of
+        views.view(S*V,H)) -> [B, 1+G1, H]: per global-map node the fused panorama of its visit, or the MEAN of the
+        candidate views that observed it; [stop] (zeros) first.  The index lists only ever name valid views, so the
+        reference's multiplication by the view mask (P/model/vilmodel_goat.py:441) is the identity on what is read."""
+        S, V, H = views.shape
+        B, G1, K = idx_v.shape
+        out = Fn.SegmentReduceFn.apply(views.reshape(S * V, H), idx_v.view(B * G1, K), True)
+        if fused is not None:
+            out = out + Fn.SegmentReduceFn.apply(fused, idx_f.view(B * G1, 1), False)
+        return torch.cat([out.new_zeros(B, 1, H), out.view(B, G1, H)], 1)
+
     def _aggregate_gmap_features(self, split_traj_embeds, split_traj_vp_lens, traj_vpids, traj_cand_vpids, gmap_vpids,
                                  split_traj_fused_embeds=None):
-        B = len(split_traj_embeds)
         step_lens = [int(x.shape[0]) for x in split_traj_embeds]
         views = torch.cat(list(split_traj_embeds), 0)                       # [S,V,H]
         S, V, H = views.shape
-        lens = torch.cat(list(split_traj_vp_lens), 0)
-        lens_h = lens.tolist()
+        lens_h = torch.cat(list(split_traj_vp_lens), 0).tolist()
         use_fused = split_traj_fused_embeds is not None
-        idx = build_gmap_index(step_lens, lens_h, traj_vpids, traj_cand_vpids, gmap_vpids, use_fused, V).to(views.device)
-        vmask = gen_seq_masks(lens, V).unsqueeze(2).to(views.dtype)
-        flat_views = (views * vmask).reshape(S * V, H)
-        fused = torch.cat(list(split_traj_fused_embeds), 0) if use_fused else views.new_zeros(S, H)
-        src = torch.cat([fused, flat_views], 0)
-        G1 = idx.shape[1]
-        out = Fn.SegmentReduceFn.apply(src, idx.view(B * G1, -1).contiguous(), True).view(B, G1, H)
-        return torch.cat([out.new_zeros(B, 1, H), out], 1)                    # [stop] token first
+        idx = build_gmap_index(step_lens, lens_h, traj_vpids, traj_cand_vpids, gmap_vpids, use_fused, V)
+        if use_fused:
+            idx_f, idx_v = split_gmap_index(idx, S)
+            fused = torch.cat(list(split_traj_fused_embeds), 0)
+        else:
+            idx_f, idx_v, fused = None, idx - S, None       # every entry is a view row (>= S); -1 - S stays negative
+        return self.aggregate_flat(views, fused, None if idx_f is None else idx_f.to(views.device), idx_v.to(views.device))
+
+    def embed_nodes(self, gmap_img_fts, gmap_step_ids, gmap_pos_fts, gmap_lens):
+        gmap_embeds = gmap_img_fts + self.step_embed(gmap_step_ids) + _pos_embed(self.gmap_pos_embeddings, gmap_pos_fts)
+        return gmap_embeds, gen_seq_masks(gmap_lens, gmap_step_ids.shape[1])
 
     def gmap_input_embedding(self, split_traj_embeds, split_traj_vp_lens, traj_vpids, traj_cand_vpids, gmap_vpids,
                              gmap_step_ids, gmap_pos_fts, gmap_lens, split_traj_fused_embeds=None):
         gmap_img_fts = self._aggregate_gmap_features(split_traj_embeds, split_traj_vp_lens, traj_vpids, traj_cand_vpids,
                                                      gmap_vpids, split_traj_fused_embeds)
-        gmap_embeds = gmap_img_fts + self.step_embed(gmap_step_ids) + _pos_embed(self.gmap_pos_embeddings, gmap_pos_fts)
-        return gmap_embeds, gen_seq_masks(gmap_lens)
+        return self.embed_nodes(gmap_img_fts, gmap_step_ids, gmap_pos_fts, gmap_lens)
 
     def step_embed(self, gmap_step_ids):
-        return torch.nn.functional.embedding(gmap_step_ids, self.gmap_step_embeddings.weight)
+        return Fn.GatherRowsFn.apply(gmap_step_ids, self.gmap_step_embeddings.weight)
 
     def sprels(self, pair_dists):
         """sprel_linear (1 -> 1) on the pairwise distances -> additive self-attention bias [B,1,G,G]"""
         if self.sprel_linear is None:
             return None
-        return (pair_dists * self.sprel_linear.weight.view(()) + self.sprel_linear.bias.view(())).unsqueeze(1)
+        return Fn.SprelFn.apply(pair_dists, self.sprel_linear.weight, self.sprel_linear.bias).unsqueeze(1)
 
     def forward(self, txt_embeds, txt_masks, split_traj_embeds, split_traj_vp_lens, traj_vpids, traj_cand_vpids,
                 gmap_vpids, gmap_step_ids, gmap_pos_fts, gmap_lens, graph_sprels=None, split_traj_fused_embeds=None):
@@ -554,13 +599,7 @@ def build_fusion_index(gmap_vpids, gmap_visited_masks, cand_vpids, n_local, firs
             else:
                 r.append([])
         rows.append(r)
-    K = max(1, max(len(e) for r in rows for e in r))
-    idx = torch.full((B, G, K), -1, dtype=torch.int32)
-    for i, r in enumerate(rows):
-        for g, e in enumerate(r):
-            if e:
-                idx[i, g, :len(e)] = torch.tensor(e, dtype=torch.int32)
-    return idx
+    return _pack_index(rows, G=G)
 
 
 def fuse_logits(global_logits, local_logits, idx):

@@ -51,14 +51,15 @@ def gen_seq_masks(seq_lens, max_len=None):
 
 def pad_tensors_wgrad(tensors, lens=None):
     """B x [T, ...] -> [B, max T, ...] zero padded, differentiable.  P/model/ops.py:46-68"""
-    if lens is None:
-        lens = [t.size(0) for t in tensors]
-    max_len = max(lens)
+    sizes = [t.size(0) for t in tensors]
+    if lens is None or [int(x) for x in lens] == sizes:
+        # one fused pad-and-stack (differentiable) instead of a cat per sample
+        return torch.nn.utils.rnn.pad_sequence(list(tensors), batch_first=True)
+    max_len = int(max(lens))
     parts = []
     for i, t in enumerate(tensors):
-        if lens[i] < max_len:
-            t = torch.cat([t, t.new_zeros((max_len - lens[i],) + tuple(t.shape[1:]))], 0)
-        parts.append(t)
+        n = int(lens[i])
+        parts.append(torch.nn.functional.pad(t[:n], (0, 0) * (t.dim() - 1) + (0, max_len - n)))
     return torch.stack(parts, 0)
 
 
@@ -133,7 +134,7 @@ class KVCache(object):
     def get(self, attn, enc, cdt):
         s = attn.self
         tag = (enc.x32.data_ptr(), tuple(enc.x32.shape), enc.x32._version, cdt, torch.is_grad_enabled(),
-               s.key.weight._version, s.value.weight._version, s.key.weight.data_ptr())
+               s.key.weight._version, s.value.weight._version, s.key.weight.data_ptr(), runtime.generation())
         e = self.entries.get(id(attn))
         if e is not None and e[0] == tag:
             self.hits += 1
@@ -215,8 +216,9 @@ class BertAttention(nn.Module):
         self.output = BertSelfOutput(config)
         self.pruned_heads = set()
 
-    def run(self, x, mask=None, enc=None, enc_mask=None):
-        """Act in, Act out (stack-internal entry point)."""
+    def run(self, x, mask=None, enc=None, enc_mask=None, bias=None):
+        """Act in, Act out (stack-internal entry point).  ``bias``: optional additive [B,Nq,Nk] / [B,1,Nq,Nk] score
+        bias of a self-attention (graph_sprels), kept apart from the key mask so neither is materialised per query."""
         x = Act.of(x)
         s, o = self.self, self.output
         cdt = runtime.compute_dtype()
@@ -226,10 +228,17 @@ class BertAttention(nn.Module):
             if enc.B != x.B:
                 raise ValueError("cross-attention batch mismatch: %d vs %d" % (x.B, enc.B))
             Nk = enc.N
-            kmask, bias = _mask_parts(enc_mask, x.B, x.N, Nk)
+            kmask, mbias = _mask_parts(enc_mask, x.B, x.N, Nk)
         else:
             Nk = x.N
-            kmask, bias = _mask_parts(mask, x.B, x.N, Nk)
+            kmask, mbias = _mask_parts(mask, x.B, x.N, Nk)
+        if bias is not None:
+            if bias.dim() == 4:
+                bias = bias[:, 0]
+            bias = bias.to(torch.float32).expand(x.B, x.N, Nk).contiguous()
+            bias = bias if mbias is None else bias + mbias
+        else:
+            bias = mbias
         seed = Fn.next_seed() if self.training else 0
         cfg = Fn.AttnCfg(x.B, x.N, Nk, s.num_attention_heads, o.LayerNorm.eps,
                          _p_drop(self.training, s.dropout.p), _p_drop(self.training, o.dropout.p), seed,
@@ -356,10 +365,8 @@ class BertCrossLayer(nn.Module):
             self.lang_output = RobertaOutput(config)
 
     def run(self, x, enc, mask=None, enc_mask=None, graph_sprels=None):
-        if graph_sprels is not None:
-            # the bias is added to the query-side mask and so only reaches self-attention (:690-698)
-            mask = graph_sprels if mask is None else mask + graph_sprels
-        a = self.attention.run(x, mask)
+        # the sprel bias is added to the query-side mask and so only reaches self-attention (:690-698)
+        a = self.attention.run(x, mask, bias=graph_sprels)
         c = self.crossattention.run(a, None, enc, enc_mask)
         return ffn_block(self.intermediate, self.output, c, self.training)
 

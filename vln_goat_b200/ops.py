@@ -15,6 +15,8 @@ LAUNCHES = [0]
 # when set to a list, every gemm() call appends (M, N, K, a_mn, b_mn, dtype code, ran_on_simt, accumulate, act, has_bias,
 # has_res, out_is_fp32, has_dropout, has_out2) -- bench.py's roofline pass re-times exactly these launches
 GEMM_LOG = None
+# same for the attention core: ("fwd" | "bwd", B, Nq, Nk, has_bias, drop_p) per call
+ATTN_LOG = None
 
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -152,6 +154,8 @@ def attn_fwd(q, k, v, heads, kmask=None, bias=None, scale=0.125, drop_p=0.0, dro
     a = _attn_args(q, k, v, o, heads, kmask, bias, scale, lse, drop_p, drop_seed, seed_ptr, force_simt)
     _lib.check(_lib.lib().goat_attn_core_fwd(C.byref(a), _stream()), "goat_attn_core_fwd")
     LAUNCHES[0] += 1
+    if ATTN_LOG is not None:
+        ATTN_LOG.append(("fwd", B, Nq, k.shape[1], int(bias is not None), float(drop_p)))
     return o, lse
 
 
@@ -169,6 +173,8 @@ def attn_bwd(do, q, k, v, o, lse, heads, dq, dk, dv, kmask=None, bias=None, scal
         dbias = torch.zeros((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
         a.dbias = dbias.data_ptr()
     _lib.check(_lib.lib().goat_attn_core_bwd(C.byref(a), _stream()), "goat_attn_core_bwd")
+    if ATTN_LOG is not None:
+        ATTN_LOG.append(("bwd", q.shape[0], q.shape[1], k.shape[1], int(bias is not None), float(drop_p)))
     # one kernel on the tcgen05 paths (16-bit, Nq <= 128), two (dQ, then dK/dV) on the fp32-math SIMT path
     LAUNCHES[0] += 1 if (q.dtype != torch.float32 and q.shape[1] <= 128 and not force_simt) else 2
     return dbias
@@ -281,9 +287,16 @@ def _f32c(t, name, shape=None):
     return t
 
 
-def attn_pool_fwd(x, w, bias, mode):
+def _nvalid(t):
+    if t is not None and (t.dtype != torch.int32 or t.numel() != 1 or not t.is_cuda):
+        raise ValueError("n_valid must be a CUDA int32 tensor with one element")
+    return t
+
+
+def attn_pool_fwd(x, w, bias, mode, n_valid=None):
     """x [B,N,H], w [H] (+ bias [1] in mode 0) -> (out [B,H], a [B,N], s [B,N] or None).  See goat_attn_pool_fwd."""
     _req_cuda(x, w, bias)
+    _nvalid(n_valid)
     B, N, H = x.shape
     _f32c(x, "x"); _f32c(w, "w"); _f32c(bias, "bias")
     if w.numel() != H:
@@ -291,20 +304,20 @@ def attn_pool_fwd(x, w, bias, mode):
     out = torch.empty((B, H), device=x.device, dtype=torch.float32)
     a = torch.empty((B, N), device=x.device, dtype=torch.float32)
     s = torch.empty((B, N), device=x.device, dtype=torch.float32) if mode == 0 else None
-    _lib.check(_lib.lib().goat_attn_pool_fwd(_p(x), _p(w), _p(bias), mode, B, N, H, _p(out), _p(a), _p(s), _stream()),
-               "goat_attn_pool_fwd")
+    _lib.check(_lib.lib().goat_attn_pool_fwd(_p(x), _p(w), _p(bias), mode, B, N, H, _p(out), _p(a), _p(s), _p(n_valid),
+                                             _stream()), "goat_attn_pool_fwd")
     LAUNCHES[0] += 1
     return out, a, s
 
 
-def attn_pool_bwd(dout, x, w, a, s, out, mode, dw, db):
+def attn_pool_bwd(dout, x, w, a, s, out, mode, dw, db, n_valid=None):
     """-> dx [B,N,H]; dw [H] / db [1] are accumulated into (pass zeroed or flat-gradient tensors)."""
     _req_cuda(dout, x, w, a, dw, db)
     B, N, H = x.shape
     _f32c(dout, "dout", (B, H)); _f32c(dw, "dw"); _f32c(db, "db")
     dx = torch.empty_like(x)
     _lib.check(_lib.lib().goat_attn_pool_bwd(_p(dout), _p(x), _p(w), _p(a), _p(s), _p(out), mode, B, N, H, _p(dx), _p(dw),
-                                             _p(db), _stream()), "goat_attn_pool_bwd")
+                                             _p(db), _p(_nvalid(n_valid)), _stream()), "goat_attn_pool_bwd")
     LAUNCHES[0] += 1
     return dx
 
@@ -406,16 +419,53 @@ def segment_reduce_fwd(src, idx, mean):
     return out
 
 
-def segment_reduce_bwd(dout, idx, mean, n_src):
-    _req_cuda(dout, idx)
+def segment_reduce_bwd(dout, idx, mean, n_src, out=None):
+    """-> dsrc [n_src,H]; with ``out`` (contiguous fp32 [n_src,H], e.g. a flat-gradient view) the result is ADDED to it"""
+    _req_cuda(dout, idx, out)
     R, K = idx.shape
     H = dout.shape[1]
     _f32c(dout, "dout", (R, H))
-    dsrc = torch.zeros((n_src, H), device=dout.device, dtype=torch.float32)
+    if out is None:
+        dsrc = torch.zeros((n_src, H), device=dout.device, dtype=torch.float32)
+    else:
+        dsrc = _f32c(out, "out", (n_src, H))
     _lib.check(_lib.lib().goat_segment_reduce_bwd(_p(dout), _p(idx), R, K, H, int(mean), _p(dsrc), _stream()),
                "goat_segment_reduce_bwd")
-    LAUNCHES[0] += 2
+    LAUNCHES[0] += 1
     return dsrc
+
+
+def act_grad(dy, ref, act, out_dtype):
+    """dy fp32 (contiguous) * act'(ref) -> new tensor of out_dtype.  ref: forward output (RELU / TANH, fp32) or the
+    stored pre-activation (GELU, fp32 / 16-bit); None for ACT_NONE (a plain cast)."""
+    _req_cuda(dy, ref)
+    if dy.dtype != torch.float32 or not dy.is_contiguous():
+        raise ValueError("act_grad: dy must be contiguous fp32")
+    if ref is not None and (not ref.is_contiguous() or ref.numel() != dy.numel()):
+        raise ValueError("act_grad: ref must be contiguous with dy's element count")
+    out = torch.empty(dy.shape, device=dy.device, dtype=out_dtype)
+    _lib.check(_lib.lib().goat_act_grad(_p(dy), _p(ref), dt(ref) if ref is not None else F32, int(act), _p(out), dt(out),
+                                        dy.numel(), _stream()), "goat_act_grad")
+    LAUNCHES[0] += 1
+    return out
+
+
+def sprel_fwd(d, w, b):
+    """d fp32 (any shape, contiguous), w / b fp32 one element each -> d * w + b"""
+    _req_cuda(d, w, b)
+    _f32c(d, "d"); _f32c(w, "w"); _f32c(b, "b")
+    out = torch.empty_like(d)
+    _lib.check(_lib.lib().goat_sprel_fwd(_p(d), _p(w), _p(b), _p(out), d.numel(), _stream()), "goat_sprel_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def sprel_bwd(dout, d, dw, db):
+    """dw[0] += sum(dout * d), db[0] += sum(dout)"""
+    _req_cuda(dout, d, dw, db)
+    _f32c(dout, "dout"); _f32c(d, "d"); _f32c(dw, "dw"); _f32c(db, "db")
+    _lib.check(_lib.lib().goat_sprel_bwd(_p(dout), _p(d), _p(dw), _p(db), d.numel(), _stream()), "goat_sprel_bwd")
+    LAUNCHES[0] += 1
 
 
 def embed_fwd(ids, word, pos, type_):

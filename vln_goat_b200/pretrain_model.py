@@ -11,6 +11,8 @@ from collections import defaultdict
 import torch
 from torch import nn
 
+from . import batching
+from . import functional as Fn
 from . import goat_blocks as G
 from . import modules as M
 from .modules import extend_neg_masks, gen_seq_masks
@@ -47,6 +49,30 @@ class GlocalTextPathCMT(nn.Module):
         return self.img_embeddings(traj_view_img_fts, traj_loc_fts, traj_nav_types, traj_step_lens, traj_vp_view_lens,
                                    self.embeddings.token_type_embeddings, z_img_features=z_img_features,
                                    z_img_pzs=z_img_pzs)
+
+    # -- index-addressed, shape-static form (batching.prepare_pretrain) ------------------------
+    def encode_prepared(self, P):
+        """-> (txt_embeds, txt_masks, views [S,V,H], fused [S,H] or None)"""
+        L = P["txt_ids"].shape[1]
+        txt_masks = gen_seq_masks(P["txt_lens"], L)
+        if self.config.do_back_txt:
+            emb, zd, zl = self.embeddings(P["txt_ids"], instr_z_direction_features=P.get("instr_z_direction_features"),
+                                          instr_z_landmark_features=P.get("instr_z_landmark_features"))
+            txt = self.lang_encoder(emb, txt_masks, z_direc_embeds=zd, z_direc_pzs=P.get("instr_z_direction_pzs"),
+                                    z_landm_embeds=zl, z_landm_pzs=P.get("instr_z_landmark_pzs"))
+        else:
+            txt = self.lang_encoder(self.embeddings(P["txt_ids"])[0], txt_masks)
+        views, _, fused = self.img_embeddings.encode(P["view_fts"], P["loc_fts"], P["view_lens"], P.get("img_z_features"),
+                                                     P.get("img_z_pzs"))
+        return txt, txt_masks, views, fused
+
+    def gmap_inputs_prepared(self, P, views, fused):
+        ge = self.global_encoder
+        img = ge.aggregate_flat(views, fused, P["gmap_idx_f"], P["gmap_idx_v"])
+        return ge.embed_nodes(img, P["gmap_step_ids"], P["gmap_pos_fts"], P["gmap_lens"])
+
+    def vp_inputs_prepared(self, P, views):
+        return self.local_encoder.vp_input_embedding_flat(views, P["view_lens"], P["last_rows"], P["vp_pos_fts"])
 
     def forward(self, txt_ids, txt_lens, traj_view_img_fts, traj_obj_img_fts, traj_loc_fts, traj_nav_types,
                 traj_step_lens, traj_vp_view_lens, traj_vp_obj_lens, traj_vpids, traj_cand_vpids, gmap_lens,
@@ -170,31 +196,51 @@ class GlocalTextPathCMTPreTraining(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def forward(self, batch, task, compute_loss=True):
+        """``batch``: the collate dict of P/data/tasks.py (tensors on the device).  The Python-list fields (viewpoint-id
+        strings, step lengths) are turned into index tensors on the host first (batching.prepare_pretrain), then the
+        shape-static device path runs (forward_prepared)."""
         batch = defaultdict(lambda: None, batch)
-        args = [batch[k] for k in _BERT_ARGS]
-        kw = dict(traj_reverie_loc_fts=batch["traj_reverie_loc_fts"], traj_reverie_obj_names=batch["traj_reverie_obj_names"],
-                  instr_z_landmark_features=batch["instr_z_landmark_features"], instr_z_landmark_pzs=batch["instr_z_landmark_pzs"],
-                  instr_z_direction_features=batch["instr_z_direction_features"],
-                  instr_z_direction_pzs=batch["instr_z_direction_pzs"], z_img_features=batch["img_z_features"],
-                  z_img_pzs=batch["img_z_pzs"])
-        if task.startswith("mlm"):
-            return self.forward_mlm(args, kw, batch["txt_labels"], compute_loss)
-        if task.startswith("sap"):
-            return self.forward_sap(args, kw, batch["gmap_visited_masks"], batch["global_act_labels"],
-                                    batch["local_act_labels"], compute_loss)
-        if task.startswith("cfp"):
-            return self.forward_cfp(args, kw, compute_loss, batch["extra_heads"])
-        if task.startswith(("mrc", "og", "valid_sap_og")):
+        task0 = task.split("_")[0]
+        if task0 in ("mrc", "og", "valid"):
             raise NotImplementedError("task %r is REVERIE-only, outside the hot-path scope" % task)
+        if task0 not in ("mlm", "sap", "cfp"):
+            raise ValueError("invalid task")
+        P = batching.prepare_pretrain(batch, task0, pad=None, pano_fusion=bool(self.config.adaptive_pano_fusion))
+        if task0 == "cfp" and not batch["extra_heads"]:
+            P["_no_extra_heads"] = True
+        return self.forward_prepared(P, task0, compute_loss)
+
+    def forward_prepared(self, P, task, compute_loss=True):
+        """P: dict of device tensors from batching.prepare_pretrain (optionally padded to static bucket shapes).
+        Returns what the reference returns: per-sample (per-masked-token) loss vector, or the logits / embeddings."""
+        if task == "mlm":
+            return self._mlm(P, compute_loss)
+        if task == "sap":
+            return self._sap(P, compute_loss)
+        if task == "cfp":
+            return self._cfp(P, compute_loss)
         raise ValueError("invalid task")
 
-    def forward_mlm(self, args, kw, txt_labels, compute_loss):
-        txt_embeds = self.bert.forward_mlm(*args, **kw)
-        sel = txt_labels != -1
-        masked_output = txt_embeds[sel]                       # only the masked tokens go through the vocabulary GEMM
+    def scalar_loss(self, P, task):
+        """mean of the loss vector over the REAL rows (``loss.mean()`` of P/train_r2r_goat.py:317; padded rows are 0)"""
+        return self.forward_prepared(P, task, True).sum() * P["loss_inv"][0]
+
+    def _mlm(self, P, compute_loss):
+        """text queries attend to the map / panorama tokens (P/model/vilmodel_goat.py:597-648), then the masked tokens
+        go through the tied vocabulary projection (P/model/pretrain_goat.py:188-224)"""
+        bert = self.bert
+        txt, txt_masks, views, fused = bert.encode_prepared(P)
+        ext_txt = extend_neg_masks(txt_masks)
+        gmap_in, gmap_masks = bert.gmap_inputs_prepared(P, views, fused)
+        g_txt = bert.global_encoder.encoder(txt, ext_txt, gmap_in, extend_neg_masks(gmap_masks))
+        vp_in, vp_masks = bert.vp_inputs_prepared(P, views)
+        v_txt = bert.local_encoder.encoder(txt, ext_txt, vp_in, extend_neg_masks(vp_masks))
+        txt_embeds = g_txt + v_txt
+        H = txt_embeds.shape[-1]
+        masked_output = Fn.SegmentReduceFn.apply(txt_embeds.reshape(-1, H), P["mlm_rows"], False)
         prediction_scores = self.mlm_head(masked_output)
         if compute_loss:
-            return G.cross_entropy(prediction_scores, txt_labels[sel])
+            return G.cross_entropy(prediction_scores, P["mlm_labels"], ignore_index=-1)
         return prediction_scores
 
     def _fuse_weights(self, gmap_embeds, vp_embeds):
@@ -202,39 +248,50 @@ class GlocalTextPathCMTPreTraining(nn.Module):
             return 0.5
         return torch.sigmoid(self.sap_fuse_linear(torch.cat([gmap_embeds[:, 0], vp_embeds[:, 0]], 1)))
 
-    def forward_sap(self, args, kw, gmap_visited_masks, global_act_labels, local_act_labels, compute_loss):
-        (txt_ids, _, _, _, _, traj_nav_types, traj_step_lens, _, _, _, traj_cand_vpids, gmap_lens, _, _, _, gmap_vpids,
-         _) = args
-        gmap_embeds, vp_embeds = self.bert(*args, **kw)
+    def _sap(self, P, compute_loss):
+        """P/model/pretrain_goat.py:286-354"""
+        bert = self.bert
+        txt, txt_masks, views, fused = bert.encode_prepared(P)
+        gmap_in, gmap_masks = bert.gmap_inputs_prepared(P, views, fused)
+        ge = bert.global_encoder
+        gmap_embeds = ge.encoder(gmap_in, gmap_masks, txt, txt_masks, graph_sprels=ge.sprels(P["gmap_pair_dists"]))
+        vp_in, vp_masks = bert.vp_inputs_prepared(P, views)
+        vp_embeds = bert.local_encoder.encoder(vp_in, vp_masks, txt, txt_masks)
         fuse_weights = self._fuse_weights(gmap_embeds, vp_embeds)
         neg_inf = -float("inf")
         global_logits = self.global_sap_head(gmap_embeds).squeeze(2) * fuse_weights
-        global_logits = global_logits.masked_fill(gmap_visited_masks, neg_inf)
-        global_logits = global_logits.masked_fill(gen_seq_masks(gmap_lens).logical_not(), neg_inf)
+        global_logits = global_logits.masked_fill(P["gmap_visited_masks"], neg_inf)
+        global_logits = global_logits.masked_fill(gmap_masks.logical_not(), neg_inf)
         local_logits = self.local_sap_head(vp_embeds).squeeze(2) * (1 - fuse_weights)
         Nq = local_logits.size(1)
-        cur_nav = torch.stack([x[-1] != 1 for x in torch.split(traj_nav_types, traj_step_lens)], 0)[:, :Nq - 1]
-        vp_nav_masks = torch.cat([cur_nav.new_zeros(len(cur_nav), 1), cur_nav], 1)      # [stop] is never masked
+        cur_nav = P["nav_types"][P["last_rows"].view(-1).long()] != 1                     # current panorama: not navigable
+        cur_nav = cur_nav[:, :Nq - 1]
+        if cur_nav.shape[1] < Nq - 1:
+            cur_nav = torch.cat([cur_nav, cur_nav.new_ones(len(cur_nav), Nq - 1 - cur_nav.shape[1])], 1)
+        vp_nav_masks = torch.cat([cur_nav.new_zeros(len(cur_nav), 1), cur_nav], 1)        # [stop] is never masked
         local_logits = local_logits.masked_fill(vp_nav_masks, neg_inf)
-        idx = G.build_fusion_index(gmap_vpids, gmap_visited_masks, [c[-1] for c in traj_cand_vpids], Nq, 1, 1)
-        fused_logits = G.fuse_logits(global_logits, local_logits, idx.to(global_logits.device))
+        fused_logits = G.fuse_logits(global_logits, local_logits, P["fuse_idx"])
+        gl, ll = P["global_act_labels"], P["local_act_labels"]
         if compute_loss:
-            return (G.cross_entropy(global_logits, global_act_labels) + G.cross_entropy(local_logits, local_act_labels) +
-                    G.cross_entropy(fused_logits, global_act_labels))
-        return global_logits, local_logits, fused_logits, global_act_labels, local_act_labels
+            return G.cross_entropy(global_logits, gl) + G.cross_entropy(local_logits, ll) + G.cross_entropy(fused_logits, gl)
+        return global_logits, local_logits, fused_logits, gl, ll
 
-    def forward_cfp(self, args, kw, compute_loss, extra_heads=False):
-        kw = dict(kw)
-        kw["return_txt_embeds"] = True
-        gmap_embeds, vp_embeds, txt_embeds = self.bert.forward_cfp(*args, **kw)
-        if extra_heads:        # a non-empty python list after collate: always true in the reference loop
+    def _cfp(self, P, compute_loss):
+        """P/model/pretrain_goat.py:467-541; the poolings run over the batch's own padded lengths (n_gmap / n_vp / n_txt)"""
+        bert = self.bert
+        txt_embeds, txt_masks, views, fused = bert.encode_prepared(P)
+        gmap_in, gmap_masks = bert.gmap_inputs_prepared(P, views, fused)
+        gmap_embeds = bert.global_encoder.tim_self_encoder(gmap_in, extend_neg_masks(gmap_masks))[0]
+        vp_in, vp_masks = bert.vp_inputs_prepared(P, views)
+        vp_embeds = bert.local_encoder.tim_self_encoder(vp_in, extend_neg_masks(vp_masks))[0]
+        if not P.get("_no_extra_heads"):        # a non-empty python list after collate: always true in the reference loop
             gmap_embeds = self.tim_global_head(gmap_embeds)
             vp_embeds = self.tim_local_head(vp_embeds)
             txt_embeds = self.tim_txt_head(txt_embeds)
         fuse_weights = self._fuse_weights(gmap_embeds, vp_embeds)
-        gmap_outputs = G.attn_pool_cfp(gmap_embeds, self.tim_global_attn)
-        vp_outputs = G.attn_pool_cfp(vp_embeds, self.tim_local_attn)
-        txt_outputs = G.attn_pool_cfp(txt_embeds, self.tim_txt_attn)
+        gmap_outputs = G.attn_pool_cfp(gmap_embeds, self.tim_global_attn, P["n_gmap"])
+        vp_outputs = G.attn_pool_cfp(vp_embeds, self.tim_local_attn, P["n_vp"])
+        txt_outputs = G.attn_pool_cfp(txt_embeds, self.tim_txt_attn, P["n_txt"])
         fused_outputs = gmap_outputs * fuse_weights + vp_outputs * (1 - fuse_weights)
         if compute_loss:
             T = self.temperature

@@ -18,6 +18,19 @@ from . import ops
 
 _compute_dtype = torch.bfloat16
 
+# Bumped by every in-place parameter update that bypasses torch's version counters (the fused optimizer kernel writes
+# through raw pointers): part of every operand-cache key below and of modules.KVCache's tags, so a cast made before the
+# update is never reused after it.
+_generation = [0]
+
+
+def generation():
+    return _generation[0]
+
+
+def bump_generation():
+    _generation[0] += 1
+
 
 def compute_dtype():
     return _compute_dtype
@@ -71,11 +84,12 @@ def wc(param, cdt=None):
     sh = getattr(param, "_goat_shadow", None)
     if sh is not None and sh.dtype == cdt:
         return sh
+    key = (param._version, _generation[0], p.data_ptr())
     ent = getattr(param, "_goat_cast", None)
-    if ent is not None and ent[0] == param._version and ent[1].dtype == cdt and ent[1].device == p.device:
+    if ent is not None and ent[0] == key and ent[1].dtype == cdt and ent[1].device == p.device:
         return ent[1]
     t = ops.cast(p.contiguous(), cdt)
-    param._goat_cast = (param._version, t)
+    param._goat_cast = (key, t)
     return t
 
 
@@ -91,7 +105,7 @@ def wc_cat(params, cdt=None):
         ds = [p.detach() for p in params]
         if _adjacent(ds):
             return _fused_view(ds)
-    key = tuple(p._version for p in params) + (cdt,)
+    key = tuple(p._version for p in params) + (cdt, _generation[0], params[0].data_ptr())
     ent = getattr(params[0], "_goat_cat", None)
     if ent is not None and ent[0] == key and ent[2] == tuple(id(p) for p in params) and ent[1].device == params[0].device:
         return ent[1]
