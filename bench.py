@@ -606,6 +606,7 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
         uniq[r] = uniq.get(r, 0) + 1
     dev = torch.device("cuda", torch.cuda.current_device())
     umma_ms, umma_flop, n_umma, simt_ms = 0.0, 0.0, 0, 0.0
+    table = []
     for (M, N, K, a_mn, b_mn, dt_, simt, acc_, act, has_bias, has_res, out32, has_drop, has_out2), cnt in uniq.items():
         dt_t = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}[dt_]
         A = (torch.randn((K, M) if a_mn else (M, K), device=dev) * 0.05).to(dt_t)
@@ -625,6 +626,9 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
         if act in (ops.ACT_DGELU, ops.ACT_DRELU):
             kw["aux_in"] = torch.randn(M, N, device=dev).to(dt_t)
         ms = _time_graph(torch, lambda: ops.gemm(A, Bm, **kw))
+        table.append((ms * cnt, "%s M=%d N=%d K=%d a_mn=%d b_mn=%d acc=%d act=%d bias=%d res=%d out32=%d drop=%d x%d  %.1f us  %.0f TFLOP/s"
+                      % ("simt" if simt else "umma", M, N, K, a_mn, b_mn, acc_, act, has_bias, has_res, out32, has_drop, cnt,
+                         ms * 1e3, 2.0 * M * N * K / (ms * 1e-3) / 1e12)))
         if simt:
             simt_ms += ms * cnt
         else:
@@ -633,6 +637,11 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
             n_umma += cnt
     achieved = umma_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
     round_ms = 3.0 * step_ms
+    if os.environ.get("GOAT_BENCH_SHAPES"):       # per-shape table, most expensive first (profiles/)
+        with open(os.environ["GOAT_BENCH_SHAPES"], "w") as f:
+            f.write("# every GEMM shape of one MLM+SAP+CFP round: total ms per round, then the launch\n")
+            for tot, line in sorted(table, reverse=True):
+                f.write("%8.3f ms  %s\n" % (tot, line))
     return {"bound": "tensor", "kernel": "gemm_umma2_kernel / gemm_umma_kernel (tcgen05.mma cta_group::2 + TMA; all %d tensor-core GEMM "
                                           "launches of one MLM+SAP+CFP round, each shape re-timed as 20 graph-captured launches)" % n_umma,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,

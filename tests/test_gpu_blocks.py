@@ -300,6 +300,38 @@ def test_c5_long_instruction_cross_layer(dtype):
         assert err < DIG[dtype] * 2, (k, err)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_c5_long_instruction_text_layer(dtype):
+    """BASELINE.json configs[4]: the TEXT side of the 512-token stress -- one RobertaLayer (self-attention over 512 / 300
+    tokens, i.e. more than 128 QUERY rows, + FFN), forward + backward against the CPU oracle.  16-bit modes run the
+    query-tiled tcgen05 attention kernels (attention_tc.cu), no SIMT fallback."""
+    from vln_goat_b200 import modules as M, runtime
+    from vln_goat_b200.config import GoatConfig
+    B, L, H = 2, 512, 768
+    gen = torch.Generator().manual_seed(18)
+    x0 = torch.randn(B, L, H, generator=gen)
+    w = torch.randn(B, L, H, generator=gen)
+    lens = torch.tensor([512, 300])
+    params = O.seeded_params(O.roberta_layer_shapes(), seed=14)
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x64 = x0.clone().requires_grad_(True)
+    m_ref = O.extend_neg_masks(O.gen_seq_masks(lens, L))
+    ref = O.roberta_layer(P, "", x64, m_ref)
+    (ref * w).sum().backward()
+    layer = _load(M.RobertaLayer(GoatConfig()), params)
+    x = _cuda_leaf(x0)
+    with runtime.compute(dtype):
+        out = layer(x, attention_mask=m_ref.cuda())[0]
+        (out * w.cuda()).sum().backward()
+    assert _rel(out, ref.detach()) < TOL[dtype]
+    assert _rel(x.grad, x64.grad) < TOL[dtype] * 2
+    got = _grads(layer)
+    for k in ("attention.self.query.weight", "attention.self.key.weight", "attention.self.value.weight", "output.dense.weight"):
+        refg = P[k].grad
+        err = (got[k].cpu() - refg).abs().max().item() / max(refg.abs().max().item(), 1e-12)
+        assert err < DIG[dtype] * 2, (k, err)
+
+
 def test_no_cpu_fallback():
     from vln_goat_b200 import modules as M
     from vln_goat_b200.config import GoatConfig

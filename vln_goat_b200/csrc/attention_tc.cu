@@ -130,6 +130,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
+  const int q0 = blockIdx.z * 128;          // this CTA's tile of 128 query rows (long instructions: Nq up to 514)
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1);
@@ -145,11 +146,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, TILE);
-    tma_load_3d(sQ, &tmQ, bar_q, h * 64, 0, b);
+    tma_load_3d(sQ, &tmQ, bar_q, h * 64, q0, b);
   }
-  const int r = tid;
+  const int r = q0 + tid;                   // global query row; the smem / TMEM row of this thread is tid
   const bool rv = r < p.Nq;
-  const bool warp_live = warp * 32 < p.Nq;
+  const bool warp_live = q0 + warp * 32 < p.Nq;
   const float* brow = p.bias ? p.bias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
   const float* krow = p.kmask ? p.kmask + (long long)b * p.Nk : nullptr;
   const unsigned long long seed = p.drop_p > 0.f ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
@@ -263,7 +264,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           pv[j] = e;
         }
-        store_row32<T>(sP, r, g * 32, pv);
+        store_row32<T>(sP, tid, g * 32, pv);
       }
     }
     fence_proxy_async();
@@ -311,7 +312,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 constexpr int BWD_SMEM = 4 * TILE + 4 * TILE + 64 + 512 + 1024;  // Q dO K V | P(2) dS(2) | barriers | key mask | alignment
 
-template <typename T>
+// KV_OUT = true : Nq <= 128, one CTA per (head, batch) produces dQ, dK and dV.
+// KV_OUT = false: Nq > 128, one CTA per (head, batch, QUERY tile) produces only its dQ rows (accumulated over the key
+//                 chunks in registers); dK / dV come from attn_bwd_tc_kv_kernel below (one CTA per KEY chunk, accumulated
+//                 over the query tiles in TMEM).  S / dP are recomputed by both passes: the tensor work of this
+//                 HBM- and latency-bound op is negligible, and no cross-CTA reduction (atomics, workspace) is needed.
+template <typename T, bool KV_OUT>
 __global__ void __launch_bounds__(TC_THREADS)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, TcArgs p) {
@@ -331,6 +337,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
+  const int q0 = blockIdx.z * 128;
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1);
@@ -346,17 +353,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, 2 * TILE);
-    tma_load_3d(sQ, &tmQ, bar_q, h * 64, 0, b);
-    tma_load_3d(sdO, &tmdO, bar_q, h * 64, 0, b);
+    tma_load_3d(sQ, &tmQ, bar_q, h * 64, q0, b);
+    tma_load_3d(sdO, &tmdO, bar_q, h * 64, q0, b);
   }
-  const int r = tid;
+  const int r = q0 + tid;                   // global query row
   const bool rv = r < p.Nq;
   const float* brow = p.bias ? p.bias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
   const float* krow = p.kmask ? p.kmask + (long long)b * p.Nk : nullptr;
   float* dbrow = p.dbias ? p.dbias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
   const unsigned long long seed = p.drop_p > 0.f ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
   const int nchunks = (p.Nk + KC - 1) / KC;
-  const int nq16 = (min(p.Nq, 128) + 15) & ~15;
+  const int nq16 = (min(p.Nq - q0, 128) + 15) & ~15;
 
   // delta_r = sum_d dO[r,d] O[r,d];  lse_r
   float delta = 0.f, lse = 0.f;
@@ -391,10 +398,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_kv, ph_kv);
       tcgen05_fence_after();
       const uint32_t idesc = make_idesc_f16(FMT, 0, 0, 128, nk16);
-      const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO), v0 = smem_u32(sV);
+      const uint32_t qs0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO), v0 = smem_u32(sV);
 #pragma unroll
       for (int k = 0; k < 4; ++k)   // S = Q K^T -> cols [0,128)
-        umma_f16(tmem, make_smem_desc_sw128(q0 + k * 32, 0, 1024), make_smem_desc_sw128(k0 + k * 32, 0, 1024), idesc,
+        umma_f16(tmem, make_smem_desc_sw128(qs0 + k * 32, 0, 1024), make_smem_desc_sw128(k0 + k * 32, 0, 1024), idesc,
                  k ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 4; ++k)   // dP = dO V^T -> cols [128,256)
@@ -434,23 +441,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         pv[j] = pd;
         dsv[j] = ds;
       }
-      store_row32<T>(sP, r, g * 32, pv);
-      store_row32<T>(sdS, r, g * 32, dsv);
+      if (KV_OUT) store_row32<T>(sP, tid, g * 32, pv);
+      store_row32<T>(sdS, tid, g * 32, dsv);
     }
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
     if (tid == 0) {
       tcgen05_fence_after();
-      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), q0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO);
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qs0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO);
       const uint32_t id_tt = make_idesc_f16(FMT, 1, 1, 128, 64);
       const uint32_t id_nt = make_idesc_f16(FMT, 0, 1, 128, 64);
-      for (int kq = 0; kq * 16 < nq16; ++kq)   // dV[key, d] = sum_q P[q,key] dO[q,d]   -> cols [0,64)
-        umma_f16(tmem, make_smem_desc_sw128(pa + kq * 2048, TILE, 1024), make_smem_desc_sw128(g0 + kq * 2048, 8192, 1024),
-                 id_tt, kq ? 1u : 0u);
-      for (int kq = 0; kq * 16 < nq16; ++kq)   // dK[key, d] = sum_q dS[q,key] Q[q,d]  -> cols [64,128)
-        umma_f16(tmem + 64, make_smem_desc_sw128(sa + kq * 2048, TILE, 1024),
-                 make_smem_desc_sw128(q0 + kq * 2048, 8192, 1024), id_tt, kq ? 1u : 0u);
+      if (KV_OUT) {
+        for (int kq = 0; kq * 16 < nq16; ++kq)   // dV[key, d] = sum_q P[q,key] dO[q,d]   -> cols [0,64)
+          umma_f16(tmem, make_smem_desc_sw128(pa + kq * 2048, TILE, 1024), make_smem_desc_sw128(g0 + kq * 2048, 8192, 1024),
+                   id_tt, kq ? 1u : 0u);
+        for (int kq = 0; kq * 16 < nq16; ++kq)   // dK[key, d] = sum_q dS[q,key] Q[q,d]  -> cols [64,128)
+          umma_f16(tmem + 64, make_smem_desc_sw128(sa + kq * 2048, TILE, 1024),
+                   make_smem_desc_sw128(qs0 + kq * 2048, 8192, 1024), id_tt, kq ? 1u : 0u);
+      }
       for (int kk = 0; kk * 16 < nk16; ++kk)   // dQ[q, d] = sum_key dS[q,key] K[key,d]  -> cols [128,192)
         umma_f16(tmem + 128, make_smem_desc_sw128(sa + (kk >> 2) * TILE + (kk & 3) * 32, 0, 1024),
                  make_smem_desc_sw128(k0 + kk * 2048, 8192, 1024), id_nt, kk ? 1u : 0u);
@@ -461,27 +470,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_after();
 
     {
-      const int key = c * KC + tid;   // this thread's TMEM lane is a KEY for dV / dK
-      const bool kv = tid < nk;
-      float t[64];
+      if (KV_OUT) {
+        const int key = c * KC + tid;   // this thread's TMEM lane is a KEY for dV / dK
+        const bool kv = tid < nk;
+        float t[64];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(t_row + g * 32, rr);
-        tmem_ld_wait();
+        for (int g = 0; g < 2; ++g) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(t_row + g * 32, rr);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+          for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+        }
+        if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dV) + (long long)b * p.sbv + (long long)key * p.ldv + h * 64, t, 1.f);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(t_row + 64 + g * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+        }
+        if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dK) + (long long)b * p.sbk + (long long)key * p.ldk + h * 64, t, p.scale);
       }
-      if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dV) + (long long)b * p.sbv + (long long)key * p.ldv + h * 64, t, 1.f);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(t_row + 64 + g * 32, rr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
-      }
-      if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dK) + (long long)b * p.sbk + (long long)key * p.ldk + h * 64, t, p.scale);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         uint32_t rr[32];
@@ -498,6 +509,183 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// dK / dV of one 128-key chunk for Nq > 128: one CTA per (head, batch, key chunk) walks the query tiles; per tile
+// S = Q_t K_c^T and dP = dO_t V_c^T are recomputed, P~ / dS go to shared memory, and dV += P~^T dO_t, dK += dS^T Q_t
+// ACCUMULATE in TMEM across the tiles (columns [256,320) / [320,384)); one store at the end.  Thread r owns query row
+// qt*128 + r while the scores are processed and key row c*128 + r in the epilogue.
+constexpr int TMEM_COLS_KV = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+attn_bwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm(smem_raw);
+  uint8_t* sQ = sm.base;
+  uint8_t* sdO = sQ + TILE;
+  uint8_t* sK = sdO + TILE;
+  uint8_t* sV = sK + TILE;
+  uint8_t* sP = sV + TILE;
+  uint8_t* sdS = sP + 2 * TILE;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sdS + 2 * TILE);
+  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_mma = bar_q + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 3);
+  float* kml = reinterpret_cast<float*>(bar_q + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y, c = blockIdx.z;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS_KV>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr int FMT = UmmaFmt<T>::value;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320;
+
+  const int nk = min(KC, p.Nk - c * KC), nk16 = (nk + 15) & ~15;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 2 * TILE);
+    tma_load_3d(sK, &tmK, bar_kv, h * 64, c * KC, b);
+    tma_load_3d(sV, &tmV, bar_kv, h * 64, c * KC, b);
+  }
+  const float* krow = p.kmask ? p.kmask + (long long)b * p.Nk : nullptr;
+  {
+    const int key = c * KC + tid;
+    kml[tid] = key < p.Nk ? (krow ? __ldg(krow + key) * LOG2E : 0.f) : -INFINITY;
+  }
+  const unsigned long long seed = p.drop_p > 0.f ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
+  const float sl2 = p.scale * LOG2E;
+  const int nqt = (p.Nq + 127) / 128;
+  uint32_t ph_q = 0, ph_mma = 0;
+  for (int qt = 0; qt < nqt; ++qt) {
+    const int q0 = qt * 128;
+    const int nq16 = (min(p.Nq - q0, 128) + 15) & ~15;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_q, 2 * TILE);
+      tma_load_3d(sQ, &tmQ, bar_q, h * 64, q0, b);
+      tma_load_3d(sdO, &tmdO, bar_q, h * 64, q0, b);
+    }
+    // this thread's query row of the tile: lse and delta = sum_d dO O
+    const int r = q0 + tid;
+    const bool rv = r < p.Nq;
+    const float* brow = p.bias ? p.bias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
+    float delta = 0.f, lse = 0.f;
+    if (rv) {
+      const long long off = (long long)b * p.sbo + (long long)r * p.ldo + h * 64;
+      const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.O) + off);
+      const uint4* pg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dO) + off);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 a = __ldg(po + q), g = __ldg(pg + q);
+        float2 x, y;
+        x = unpack2<T>(a.x); y = unpack2<T>(g.x); delta += x.x * y.x + x.y * y.y;
+        x = unpack2<T>(a.y); y = unpack2<T>(g.y); delta += x.x * y.x + x.y * y.y;
+        x = unpack2<T>(a.z); y = unpack2<T>(g.z); delta += x.x * y.x + x.y * y.y;
+        x = unpack2<T>(a.w); y = unpack2<T>(g.w); delta += x.x * y.x + x.y * y.y;
+      }
+      lse = p.lse[((long long)b * p.heads + h) * p.Nq + r] * LOG2E;
+    }
+    if (tid == 0) {
+      if (qt == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph_q);
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_f16(FMT, 0, 0, 128, nk16);
+      const uint32_t qs0 = smem_u32(sQ), k0 = smem_u32(sK), g0 = smem_u32(sdO), v0 = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem + COL_S, make_smem_desc_sw128(qs0 + k * 32, 0, 1024), make_smem_desc_sw128(k0 + k * 32, 0, 1024),
+                 idesc, k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem + COL_DP, make_smem_desc_sw128(g0 + k * 32, 0, 1024), make_smem_desc_sw128(v0 + k * 32, 0, 1024),
+                 idesc, k ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    ph_q ^= 1;
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tcgen05_fence_after();
+    __syncthreads();     // kml visible (first tile)
+    for (int g = 0; g * 32 < nk16; ++g) {
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32b_x32(t_row + COL_S + g * 32, rs);
+      tmem_ld_32x32b_x32(t_row + COL_DP + g * 32, rp);
+      tmem_ld_wait();
+      float pv[32], dsv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int key = c * KC + g * 32 + j;
+        float pd = 0.f, ds = 0.f;
+        if (rv && key < p.Nk) {
+          float s = fmaf(__uint_as_float(rs[j]), sl2, kml[g * 32 + j]);
+          if (brow) s = fmaf(__ldg(brow + key), LOG2E, s);
+          const float pr = ex2_approx(s - lse);
+          const float dm = p.drop_p > 0.f ? drop_mul(p, seed, b, h, r, key) : 1.f;
+          pd = pr * dm;
+          ds = pr * (__uint_as_float(rp[j]) * dm - delta);
+        }
+        pv[j] = pd;
+        dsv[j] = ds;
+      }
+      store_row32<T>(sP, tid, g * 32, pv);
+      store_row32<T>(sdS, tid, g * 32, dsv);
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qs0 = smem_u32(sQ), g0 = smem_u32(sdO);
+      const uint32_t id_tt = make_idesc_f16(FMT, 1, 1, 128, 64);
+      for (int kq = 0; kq * 16 < nq16; ++kq)   // dV[key, d] += sum_q P~[q,key] dO[q,d]
+        umma_f16(tmem + COL_DV, make_smem_desc_sw128(pa + kq * 2048, TILE, 1024),
+                 make_smem_desc_sw128(g0 + kq * 2048, 8192, 1024), id_tt, (qt | kq) ? 1u : 0u);
+      for (int kq = 0; kq * 16 < nq16; ++kq)   // dK[key, d] += sum_q dS[q,key] Q[q,d]
+        umma_f16(tmem + COL_DK, make_smem_desc_sw128(sa + kq * 2048, TILE, 1024),
+                 make_smem_desc_sw128(qs0 + kq * 2048, 8192, 1024), id_tt, (qt | kq) ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma);    // Q / dO / P / dS tiles may be overwritten by the next query tile
+    ph_mma ^= 1;
+    tcgen05_fence_after();
+    tcgen05_fence_before();
+    __syncthreads();
+  }
+  {
+    const int key = c * KC + tid;
+    const bool kv = tid < nk;
+    float t[64];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(t_row + COL_DV + g * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+    }
+    if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dV) + (long long)b * p.sbv + (long long)key * p.ldv + h * 64, t, 1.f);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(t_row + COL_DK + g * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[g * 32 + j] = __uint_as_float(rr[j]);
+    }
+    if (kv) store_global_row64<T>(reinterpret_cast<T*>(p.dK) + (long long)b * p.sbk + (long long)key * p.ldk + h * 64, t, p.scale);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TMEM_COLS_KV>(tmem);
 }
 
 int fill(const goat_attn_args* a, TcArgs* t) {
@@ -529,7 +717,7 @@ int fwd_launch(const goat_attn_args* a, cudaStream_t st) {
   if ((rc = make_tmap3(&tv, a->dtype, a->V, cols, a->Nk, a->B, a->ldv, a->sbv, 64, 128))) return rc;
   TcArgs t;
   fill(a, &t);
-  dim3 grid(a->heads, a->B);
+  dim3 grid(a->heads, a->B, (a->Nq + 127) / 128);
   attn_fwd_tc_kernel<T><<<grid, TC_THREADS, FWD_SMEM, st>>>(tq, tk, tv, t);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
@@ -539,7 +727,9 @@ template <typename T>
 int bwd_launch(const goat_attn_args* a, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) {
-    GOAT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    GOAT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    GOAT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    GOAT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     cfg = true;
   }
   CUtensorMap tq, tk, tv, tg;
@@ -551,8 +741,18 @@ int bwd_launch(const goat_attn_args* a, cudaStream_t st) {
   if ((rc = make_tmap3(&tg, a->dtype, a->dO, cols, a->Nq, a->B, a->ldo, a->sbo, 64, 128))) return rc;
   TcArgs t;
   fill(a, &t);
-  dim3 grid(a->heads, a->B);
-  attn_bwd_tc_kernel<T><<<grid, TC_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tg, t);
+  if (a->Nq <= 128) {
+    dim3 grid(a->heads, a->B);
+    attn_bwd_tc_kernel<T, true><<<grid, TC_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tg, t);
+    GOAT_LAUNCH_CHECK();
+    return GOAT_OK;
+  }
+  // long query sequences (RxR / 512-token instructions): dQ per query tile, then dK / dV per key chunk
+  dim3 gq(a->heads, a->B, (a->Nq + 127) / 128);
+  attn_bwd_tc_kernel<T, false><<<gq, TC_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tg, t);
+  GOAT_LAUNCH_CHECK();
+  dim3 gk(a->heads, a->B, (a->Nk + KC - 1) / KC);
+  attn_bwd_tc_kv_kernel<T><<<gk, TC_THREADS, BWD_SMEM, st>>>(tq, tk, tv, tg, t);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
@@ -563,11 +763,12 @@ bool ok16(const void* p, long long ld, long long sb) {
 
 }  // namespace
 
-// The tensor-core path takes 16-bit operands, up to 128 query rows per (head, batch) and TMA-compatible strides.
+// The tensor-core path takes 16-bit operands and TMA-compatible strides; any number of query rows / keys (128-row
+// query tiles on grid.z, 128-key chunks in the kernel).
 bool attn_tc_eligible(const goat_attn_args* a, bool bwd) {
   if (a->dtype != GOAT_F16 && a->dtype != GOAT_BF16) return false;
-  if (a->Nq > 128 || a->Nq < 1 || a->Nk < 1 || a->D != 64) return false;
-  if (a->heads > 65535 || a->B > 65535) return false;
+  if (a->Nq < 1 || a->Nk < 1 || a->D != 64) return false;
+  if (a->heads > 65535 || a->B > 65535 || a->Nq > 65535 * 128 || a->Nk > 65535 * 128) return false;
   if (a->B > 1 && (a->sbq <= 0 || a->sbk <= 0 || a->sbv <= 0 || a->sbo <= 0)) return false;  // broadcast operands
   if (!ok16(a->Q, a->ldq, a->sbq) || !ok16(a->K, a->ldk, a->sbk) || !ok16(a->V, a->ldv, a->sbv) ||
       !ok16(a->O, a->ldo, a->sbo))

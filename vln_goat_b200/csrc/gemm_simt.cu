@@ -12,8 +12,8 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, EpiParams ep, int M, int N, int K, long long sAm,
-                 long long sAk, long long sBn, long long sBk) {
+gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, EpiParams ep, int M, int N, int Kfull, long long sAm,
+                 long long sAk, long long sBn, long long sBk, int k_chunk) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -27,7 +27,10 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, EpiParams ep,
 
   // loader mapping: pick the thread->element order that makes global reads contiguous
   const bool a_kfast = (sAk == 1), b_kfast = (sBk == 1);
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  // split-K (accumulate mode only): grid.z slices of k_chunk; every slice adds its partial product with atomics
+  const int kbeg = blockIdx.z * k_chunk;
+  const int K = min(Kfull, kbeg + k_chunk);
+  for (int k0 = kbeg; k0 < K; k0 += TK) {
 #pragma unroll
     for (int t = 0; t < (TM * TK) / 256; ++t) {
       const int e = tid + t * 256;
@@ -84,8 +87,22 @@ int launch_simt(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t strea
   const long long sAm = a.a_mn_major ? 1 : a.lda, sAk = a.a_mn_major ? a.lda : 1;
   const long long sBn = a.b_mn_major ? 1 : a.ldb, sBk = a.b_mn_major ? a.ldb : 1;
   dim3 grid((a.N + TN - 1) / TN, (a.M + TM - 1) / TM);
+  int k_chunk = a.K;
+  if (ep.accumulate) {
+    // weight gradients of the narrow layers (7 / 14-wide position features, 1-wide heads) are [few tiles] x [K = all tokens]:
+    // split K so that about four waves of CTAs exist instead of a dozen CTAs walking thousands of k-steps each
+    const long long tiles = (long long)grid.x * grid.y;
+    long long want = (4 * 148 + tiles - 1) / tiles;
+    const long long cap = (a.K + 4 * TK - 1) / (4 * TK);     // at least 64 of K per slice
+    if (want > cap) want = cap;
+    if (want > 65535) want = 65535;
+    if (want > 1) {
+      k_chunk = (int)(((a.K + want - 1) / want + TK - 1) / TK * TK);
+      grid.z = (unsigned)((a.K + k_chunk - 1) / k_chunk);
+    }
+  }
   gemm_simt_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(a.A), reinterpret_cast<const T*>(a.B), ep,
-                                                 a.M, a.N, a.K, sAm, sAk, sBn, sBk);
+                                                 a.M, a.N, a.K, sAm, sAk, sBn, sBk, k_chunk);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
