@@ -294,12 +294,69 @@ def gen_nav_rollout():
     save("nav_rollout", **arrs, **grads_digest(model))
 
 
+def gen_nav_branches():
+    """The configuration branches the shipped scripts leave off but the code carries: BACL text type_1 and type_2 with
+    the 'add' / 'concat' merges (M/models/vilmodel_GOAT.py:107-160), BACL image type_2 with door / add / concat (:661-683,
+    run through the reference's own ``forward_panorama_do_per_step`` on a stand-in object that owns the reference
+    ``CausalImageEmbeddings``).  Outputs are stored on every 4th token (plus a digest of the whole tensor) to keep the
+    fixture small; input-gradient digests are stored too."""
+    ref_shim.install("nav")
+    import types
+    import models.vilmodel_GOAT as V
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    txt = torch.randn(2, 28, 768, generator=g)
+    zd = torch.randn(2, 35, 768, generator=g)
+    zl = torch.randn(2, 39, 768, generator=g)
+    ft = torch.tanh(torch.randn(2, 24, 768, generator=g))
+    tl = torch.tensor([28, 19])
+
+    def pz(n):
+        p = torch.rand(2, n, 1, generator=g, dtype=torch.float64)
+        return p / p.sum(1, keepdim=True)
+    pzd, pzl = pz(35), pz(39)
+    w_txt = torch.randn(2, 28, 768, generator=g)
+    out.update(txt=txt, z_direc=zd, z_landm=zl, front_txt=ft, txt_lens=tl.numpy(), pz_direc=pzd, pz_landm=pzl, w_txt=w_txt)
+    for tag, kw in (("t1", dict(do_back_txt_type="type_1")),
+                    ("t2add", dict(do_back_txt_type="type_2", do_add_method="add")),
+                    ("t2cat", dict(do_back_txt_type="type_2", do_add_method="concat"))):
+        cfg = ref_shim.nav_config(**kw)
+        le = load_seeded(V.LanguageEncoderDo(cfg).eval(), seed=41)
+        t_ = txt.clone().requires_grad_(True)
+        y = le(t_, O.gen_seq_masks(tl, 28), zd, pzd, zl, pzl, ft)
+        (y * w_txt).sum().backward()
+        out["txt_%s_out" % tag] = y[:, ::4]
+        out["txt_%s_dig" % tag] = digest(y)
+        out["txt_%s_dx_dig" % tag] = digest(t_.grad)
+    view = torch.randn(2, 36, 768, generator=g)
+    loc = torch.randn(2, 36, 7, generator=g)
+    zf = torch.randn(2, 50, 768, generator=g)
+    pzi = pz(50)
+    vl = torch.tensor([36, 31])
+    w_v = torch.randn(2, 36, 768, generator=g)
+    out.update(view=view, loc=loc, z_img=zf, pz_img=pzi, view_lens=vl.numpy(), w_view=w_v)
+    for tag, kw in (("door", dict(do_back_img_type="type_2", do_add_method="door")),
+                    ("add", dict(do_back_img_type="type_2", do_add_method="add")),
+                    ("cat", dict(do_back_img_type="type_2", do_add_method="concat"))):
+        cfg = ref_shim.nav_config(**kw)
+        ie = load_seeded(V.CausalImageEmbeddings(cfg).eval(), seed=42)
+        holder = types.SimpleNamespace(img_embeddings=ie, config=cfg)
+        v_ = view.clone().requires_grad_(True)
+        pe, pm, pf = V.GlocalTextPathNavCMT.forward_panorama_do_per_step(holder, v_, loc, None, vl, zf, pzi)
+        ((pe * w_v).sum() + pf.sum()).backward()
+        out["img_%s_out" % tag] = pe[:, ::4]
+        out["img_%s_dig" % tag] = digest(pe)
+        out["img_%s_fused" % tag] = pf
+        out["img_%s_dx_dig" % tag] = digest(v_.grad)
+    save("nav_branches", **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tree", choices=["pretrain", "nav", "pretrain_full", "nav_full", "nav_rollout", "all"], default="all")
+    ap.add_argument("--tree", choices=["pretrain", "nav", "pretrain_full", "nav_full", "nav_rollout", "nav_branches", "all"], default="all")
     a = ap.parse_args()
     if a.tree == "all":
-        for t in ("pretrain", "nav", "pretrain_full", "nav_full", "nav_rollout"):
+        for t in ("pretrain", "nav", "pretrain_full", "nav_full", "nav_rollout", "nav_branches"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "--tree", t])
     elif a.tree == "pretrain":
         gen_pretrain()
@@ -309,5 +366,7 @@ if __name__ == "__main__":
         gen_nav_full()
     elif a.tree == "nav_rollout":
         gen_nav_rollout()
+    elif a.tree == "nav_branches":
+        gen_nav_branches()
     else:
         gen_nav()

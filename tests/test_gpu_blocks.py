@@ -332,6 +332,119 @@ def test_c5_long_instruction_text_layer(dtype):
         assert err < DIG[dtype] * 2, (k, err)
 
 
+# ----------------------------------------------------------------------------------------------
+# causal-intervention blocks in isolation, against fixtures of the unmodified reference classes
+# ----------------------------------------------------------------------------------------------
+def _nav_cfg(**kw):
+    from vln_goat_b200.config import GoatConfig
+    base = dict(layer_norm_eps=1e-5, pad_token_id=1, dataset="r2r", mode="train", obj_feat_size=0, feat_dropout=0.4,
+                do_back_img=True, do_back_txt=True, do_front_img=True, do_front_his=True, do_front_txt=True,
+                do_back_txt_type="type_2", do_back_img_type="type_1", do_add_method="door", use_lang2visn_attn=False)
+    base.update(kw)
+    return GoatConfig(**base)
+
+
+def _seeded(module, seed):
+    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    module.load_state_dict(O.seeded_params(shapes, seed=seed), strict=True)
+    return module.cuda().eval()
+
+
+def _digest_close(t, ref, rtol):
+    from tests.helpers import digest
+    d = digest(t)
+    scale = ref[1].abs().item() + 1e-30
+    return bool(((d[:3] - ref.double()[:3]).abs() <= rtol * scale + 1e-4).all())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_front_door_encoder_block(dtype):
+    """FACL FrontDoorEncoder (M/models/vilmodel_GOAT.py:526-554): self-attention + cross-attention onto the 24 prototypes,
+    LN, door gate; output, input gradient and the 26 parameter-gradient digests of the reference."""
+    from vln_goat_b200 import goat_blocks as G, runtime
+    g = golden("front_door")
+    fd = _seeded(G.FrontDoorEncoder(_nav_cfg()), 7)
+    x = _cuda_leaf(g["x"])
+    with runtime.compute(dtype):
+        out = fd(x, g["proto"].cuda(), O.gen_seq_masks(g["lens"], 38).cuda())
+        (out * g["w_out"].cuda()).sum().backward()
+    assert _rel(out, g["out"]) < TOL[dtype]
+    assert _rel(x.grad, g["dx"]) < TOL[dtype] * 2
+    assert_digests(g, _grads(fd), rtol=DIG[dtype] * 2, key_bias_atol=KB[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_language_encoder_do_block(dtype):
+    """LanguageEncoderDo (6 RobertaLayers + BACL text type_2 + FACL text, door merge; M/models/vilmodel_GOAT.py:55-162)."""
+    from vln_goat_b200 import goat_blocks as G, runtime
+    g = golden("lang_encoder_do")
+    le = _seeded(G.LanguageEncoderDo(_nav_cfg()), 8)
+    txt = _cuda_leaf(g["txt"])
+    with runtime.compute(dtype):
+        out = le(txt, O.gen_seq_masks(g["txt_lens"], 44).cuda(), g["z_direc"].cuda(), None, g["z_landm"].cuda(), None,
+                 g["front_txt"].cuda())
+        (out * g["w_out"].cuda()).sum().backward()
+    assert _rel(out, g["out"]) < TOL[dtype] * 2           # 6 layers + two intervention stages deep
+    assert _rel(txt.grad, g["dtxt"]) < TOL[dtype] * 4
+    assert_digests(g, _grads(le), rtol=DIG[dtype] * 3, atol=1e-3 if dtype == torch.float32 else 3e-2, key_bias_atol=KB[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_bacl_image_type1_block(dtype):
+    """CausalImageEmbeddings.back_door, type_1 (M/models/vilmodel_GOAT.py:661-667)."""
+    from vln_goat_b200 import goat_blocks as G, runtime
+    g = golden("bacl_image")
+    ie = _seeded(G.CausalImageEmbeddings(_nav_cfg()), 9)
+    with runtime.compute(dtype), torch.no_grad():
+        out = ie.back_door(g["view"].cuda(), g["zf"].cuda(), g["pz"].cuda())
+    assert _rel(out, g["out"]) < TOL[dtype]
+
+
+BRANCH_TOL = {torch.float32: 2e-5, torch.float16: 2e-3}      # 6 text layers / 2 pano layers below the branch under test
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("tag,kw", [("t1", dict(do_back_txt_type="type_1")),
+                                    ("t2add", dict(do_back_txt_type="type_2", do_add_method="add")),
+                                    ("t2cat", dict(do_back_txt_type="type_2", do_add_method="concat"))])
+def test_language_encoder_do_other_branches(tag, kw, dtype):
+    """BACL text type_1 (p(z)-weighted dictionary sums) and the type_2 'add' / 'concat' merges, which the shipped scripts
+    leave off: fixtures from the reference class under those configs (tests/golden/make_golden.py --tree nav_branches)."""
+    from vln_goat_b200 import goat_blocks as G, runtime
+    g = golden("nav_branches")
+    le = _seeded(G.LanguageEncoderDo(_nav_cfg(**kw)), 41)
+    txt = _cuda_leaf(g["txt"])
+    with runtime.compute(dtype):
+        out = le(txt, O.gen_seq_masks(g["txt_lens"], 28).cuda(), g["z_direc"].cuda(), g["pz_direc"].cuda(),
+                 g["z_landm"].cuda(), g["pz_landm"].cuda(), g["front_txt"].cuda())
+        (out * g["w_txt"].cuda()).sum().backward()
+    assert _rel(out[:, ::4], g["txt_%s_out" % tag]) < BRANCH_TOL[dtype]
+    assert _digest_close(out, g["txt_%s_dig" % tag], DIG[dtype] * 2)
+    assert _digest_close(txt.grad, g["txt_%s_dx_dig" % tag], DIG[dtype] * 4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("tag,kw", [("door", dict(do_back_img_type="type_2", do_add_method="door")),
+                                    ("add", dict(do_back_img_type="type_2", do_add_method="add")),
+                                    ("cat", dict(do_back_img_type="type_2", do_add_method="concat"))])
+def test_bacl_image_type2_branches_through_panorama(tag, kw, dtype):
+    """BACL image type_2 (cross-attention onto the image dictionary, door / add / concat merge) through the whole per-step
+    panorama path (embedding + location + 2-layer pano encoder + adaptive fusion), vs the reference's
+    forward_panorama_do_per_step under those configs."""
+    from vln_goat_b200 import goat_blocks as G, runtime
+    g = golden("nav_branches")
+    ie = _seeded(G.CausalImageEmbeddings(_nav_cfg(**kw)), 42)
+    view = _cuda_leaf(g["view"])
+    with runtime.compute(dtype):
+        pe, pm, pf = ie.encode(view, g["loc"].cuda(), g["view_lens"].cuda(), g["z_img"].cuda(), g["pz_img"].cuda(),
+                               loc_after_do=True)
+        ((pe * g["w_view"].cuda()).sum() + pf.sum()).backward()
+    assert _rel(pe[:, ::4], g["img_%s_out" % tag]) < BRANCH_TOL[dtype]
+    assert _rel(pf, g["img_%s_fused" % tag]) < BRANCH_TOL[dtype]
+    assert _digest_close(pe, g["img_%s_dig" % tag], DIG[dtype] * 2)
+    assert _digest_close(view.grad, g["img_%s_dx_dig" % tag], DIG[dtype] * 4)
+
+
 def test_no_cpu_fallback():
     from vln_goat_b200 import modules as M
     from vln_goat_b200.config import GoatConfig
