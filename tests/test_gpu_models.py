@@ -379,19 +379,27 @@ def test_padded_prepared_batch_gives_the_same_rows(dtype):
             b = model.forward_prepared(P1, task, compute_loss=False)
             la = model.forward_prepared(P0, task, compute_loss=True)
             lb = model.forward_prepared(P1, task, compute_loss=True)
+            # fp32 (SIMT kernels): bit-identical.  fp16: the panorama tokens go through GEMM launches of a different M
+            # (more padded steps), whose fp32 results differ in the last bits (measured 3e-6); every later 16-bit rounding
+            # can turn that into one fp16 ulp, so the 16-bit mode is held to the 16-bit tolerance instead
+            def same(x, y):
+                if dtype == torch.float32:
+                    return torch.equal(x, y)
+                fin = torch.isfinite(x)
+                return torch.equal(fin, torch.isfinite(y)) and _rel(y[fin], x[fin].cpu()) < 2e-3
             if task == "mlm":
                 n = a.shape[0]
-                assert torch.equal(a, b[:n]) and torch.equal(la, lb[:n]) and float(lb[n:].abs().max()) == 0.0
+                assert same(a, b[:n]) and same(la, lb[:n]) and float(lb[n:].abs().max()) == 0.0
             elif task == "sap":
                 G = a[0].shape[1]
-                assert torch.equal(a[0], b[0][:, :G]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2][:, :G])
-                assert bool(torch.isinf(b[0][:, G:]).all()) and torch.equal(la, lb)
+                assert same(a[0], b[0][:, :G]) and same(a[1], b[1]) and same(a[2], b[2][:, :G])
+                assert bool(torch.isinf(b[0][:, G:]).all()) and same(la, lb)
             else:
                 for x, y in zip(a, b):
-                    assert torch.equal(x, y)
-                assert torch.equal(la, lb)
+                    assert same(x, y)
+                assert same(la, lb)
             sa, sb = model.scalar_loss(P0, task), model.scalar_loss(P1, task)
-            assert abs(sa.item() - sb.item()) <= 1e-6 * max(1.0, abs(sa.item()))
+            assert abs(sa.item() - sb.item()) <= (1e-6 if dtype == torch.float32 else 2e-3) * max(1.0, abs(sa.item()))
 
 
 def _oracle_leaves(model):

@@ -421,7 +421,10 @@ int dispatch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) 
 
 bool gemm_umma_eligible(const goat_gemm_args& a) {
   if (a.dtype != GOAT_F16 && a.dtype != GOAT_BF16) return false;
-  if (a.K < 16 || (a.K & 7) || (a.lda & 7) || (a.ldb & 7)) return false;
+  // TMA needs 16-byte global strides (leading dimensions multiples of 8 elements); the extents themselves may be ragged
+  // (out-of-range elements are zero-filled), so K need not be a multiple of 8 once the rows are padded -- the
+  // 50265-wide vocabulary gradient is read that way
+  if (a.K < 16 || (a.lda & 7) || (a.ldb & 7)) return false;
   if (!aligned16(a.A) || !aligned16(a.B)) return false;
   return true;
 }

@@ -408,10 +408,17 @@ class PanoLayerFn(torch.autograd.Function):
                 None)
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b), act in {none, relu, tanh, gelu}; fp32 in / fp32 out, GEMM in the compute dtype.
     Shapes the tcgen05 path cannot take (K or N tiny: 7/14-wide position features, 1-wide heads) run on
-    the fp32 SIMT kernel regardless of the compute dtype."""
+    the fp32 SIMT kernel regardless of the compute dtype.  A wide output whose width is not a multiple of 8 (the
+    50265-wide vocabulary projection) is produced into a row-padded buffer and returned as a view: the leading
+    dimension stays a multiple of 8, so the epilogue stores vectors and the backward GEMMs (whose K / M dimension is
+    that width) can read the 16-bit gradient through TMA instead of falling to the SIMT kernel."""
 
     @staticmethod
     def forward(ctx, x32, x16, W, b, W_c, act, cdt):
@@ -420,10 +427,14 @@ class LinearFn(torch.autograd.Function):
             cdt = torch.float32
             W_c = W
         xc = _c(x32, x16, cdt)
+        M, N = xc.shape[0], W.shape[0]
         aux = None
         if act == ops.ACT_GELU:
-            aux = torch.empty((xc.shape[0], W.shape[0]), device=xc.device, dtype=cdt)
-        y = ops.gemm(xc, W_c, bias=b, act=act, aux_out=aux, out_dtype=torch.float32)
+            aux = torch.empty((M, N), device=xc.device, dtype=cdt)
+        out = None
+        if N % 8 != 0 and N >= 256 and cdt != torch.float32:
+            out = torch.empty((M, _pad8(N)), device=xc.device, dtype=torch.float32)[:, :N]
+        y = ops.gemm(xc, W_c, bias=b, act=act, aux_out=aux, out=out, out_dtype=torch.float32)
         ctx.act, ctx.cdt = act, cdt
         ctx.params = (W, b)
         ctx.has_bias = b is not None
@@ -434,13 +445,22 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         xc, W_c, y, aux = ctx.saved_tensors
         cdt = ctx.cdt
-        dy = dy.contiguous()
-        if ctx.act in (ops.ACT_RELU, ops.ACT_TANH):
-            dyc = ops.act_grad(dy, y, ctx.act, cdt)          # dy * act'(y), converted to the operand dtype, one kernel
-        elif ctx.act == ops.ACT_GELU:
-            dyc = ops.act_grad(dy, aux, ctx.act, cdt)
+        M, N = dy.shape
+        padded = (dy.dim() == 2 and dy.stride(1) == 1 and dy.stride(0) == _pad8(N) and dy.stride(0) != N and
+                  ctx.act == ops.ACT_NONE)
+        if padded:
+            # gradient of a row-padded output (see forward): convert the whole padded block, keep the leading dimension
+            Np = dy.stride(0)
+            base = dy.as_strided((M, Np), (Np, 1))
+            dyc = (base if cdt == torch.float32 else ops.cast(base, cdt))[:, :N]
         else:
-            dyc = dy if cdt == torch.float32 else ops.cast(dy, cdt)
+            dy = dy.contiguous()
+            if ctx.act in (ops.ACT_RELU, ops.ACT_TANH):
+                dyc = ops.act_grad(dy, y, ctx.act, cdt)          # dy * act'(y), converted to the operand dtype, one kernel
+            elif ctx.act == ops.ACT_GELU:
+                dyc = ops.act_grad(dy, aux, ctx.act, cdt)
+            else:
+                dyc = dy if cdt == torch.float32 else ops.cast(dy, cdt)
         W, b = ctx.params
         db, = _bgrad((b,), dyc)
         dW, = _wgrad((W,), dyc, xc)
@@ -575,7 +595,13 @@ class XentFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         logits, labels, lse = ctx.saved_tensors
-        return ops.xent_bwd(dloss.contiguous(), logits, labels, lse, ctx.ignore_index), None, None
+        out = None
+        if logits.stride(1) == 1 and logits.stride(0) != logits.shape[1]:
+            # row-padded logits (LinearFn): the gradient keeps the padded leading dimension; the pad columns are zeroed
+            # because the consumer converts the whole padded block
+            Np = logits.stride(0)
+            out = torch.zeros((logits.shape[0], Np), device=logits.device, dtype=torch.float32)[:, :logits.shape[1]]
+        return ops.xent_bwd(dloss.contiguous(), logits, labels, lse, ctx.ignore_index, out=out), None, None
 
 
 class SegmentReduceFn(torch.autograd.Function):

@@ -71,6 +71,16 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
             out = torch.zeros((M, N), device=A.device, dtype=torch.float32)
         else:
             out = torch.empty((M, N), device=A.device, dtype=out_dtype or A.dtype)
+    if (not accumulate and A.dtype == torch.float32 and K >= 256 and ((M + 63) // 64) * ((N + 63) // 64) <= 64
+            and act == ACT_NONE and res is None and drop_p == 0.0 and out2 is None and aux_out is None and alpha == 1.0
+            and out.dtype == torch.float32 and out.is_contiguous()):
+        # a few output tiles and a long reduction on the fp32 SIMT kernel (B x B InfoNCE similarities, 1-wide heads on a
+        # few rows): start from the bias and let the split-K slices add their partial products
+        if bias is None:
+            out.zero_()
+        else:
+            out.copy_(bias.unsqueeze(0).expand(M, N))
+        bias, accumulate = None, True
     a = _lib.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.dtype = dt(A)
@@ -104,7 +114,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
     _lib.check(_lib.lib().goat_gemm(C.byref(a), _stream()), "goat_gemm")
     LAUNCHES[0] += 1
     if GEMM_LOG is not None:
-        umma = a.dtype != F32 and K >= 16 and K % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and not force_simt
+        umma = a.dtype != F32 and K >= 16 and lda % 8 == 0 and ldb % 8 == 0 and not force_simt
         GEMM_LOG.append((M, N, K, int(a_mn), int(b_mn), a.dtype, int(not umma), int(accumulate), int(act), int(bias is not None),
                          int(res is not None), int(out.dtype == torch.float32), int(drop_p > 0.0), int(out2 is not None)))
     return out
