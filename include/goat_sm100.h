@@ -256,6 +256,21 @@ int goat_xent_bwd(const float* dloss, const float* logits, long long stride_row,
                   const long long* labels, const float* lse, int M, int N, long long ignore_index, float* dlogits,
                   long long dstride_row, long long dstride_col, int accumulate, goat_stream_t stream);
 
+/* The same cross-entropy over a class axis that is only ever materialised one column chunk at a time -- the MLM head's
+ * tied 768 -> 50265 vocabulary projection (P/model/Bert_backbone.py:813-829, loss P/model/pretrain_goat.py:209-224), whose
+ * [n, 50265] fp32 logits the reference writes to memory and reads back three times.
+ *   fwd (per chunk [c0, c0+Nc) of the logits, `first` = 1 on the first chunk): running row maximum / sum of exponentials
+ *       (run_max, run_sum [M]) and the label's logit (picked [M]) are updated; afterwards lse = run_max + log(run_sum) and
+ *       loss = lse - picked (0 for label == ignore_index).
+ *   bwd (per recomputed chunk): out[i,j] = dloss_i (exp(logit_ij - lse_i) - [c0 + j == label_i]) converted to out_dtype
+ *       with leading dimension ldo -- directly the operand of the dgrad / wgrad GEMMs.  Labels outside [0, n_classes)
+ *       other than ignore_index give no gradient. */
+int goat_xent_chunk_fwd(const float* logits, long long ld, const long long* labels, int M, int Nc, long long c0, int first,
+                        float* run_max, float* run_sum, float* picked, goat_stream_t stream);
+int goat_xent_chunk_bwd(const float* dloss, const float* logits, long long ld, const long long* labels, const float* lse,
+                        int M, int Nc, long long c0, long long ignore_index, long long n_classes, void* out, int out_dtype,
+                        long long ldo, goat_stream_t stream);
+
 /* Gather-and-reduce over index lists: out[r,:] = scale * sum_{k<K, idx[r,k]>=0} src[idx[r,k],:], scale = 1 (sum) or
  * 1/#valid (mean).  Replaces the host Python loops of global-map aggregation (P/model/vilmodel_goat.py:430-468: mean
  * of the candidate-view embeddings that observed an unvisited node) and of the SAP / navigation logit fusion

@@ -557,3 +557,52 @@ def test_attn_pool_n_valid_ignores_extra_padding():
         assert torch.equal(a, b)
         assert maxerr(xa.grad[:, :17], xb.grad) < 1e-6 and float(xa.grad[:, 17:].abs().max()) == 0.0
         assert maxerr(wv.grad, wr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_chunked_vocab_cross_entropy_matches_materialised_logits(dtype):
+    """the MLM head's fused, chunked vocabulary projection + cross-entropy (functional.VocabXentFn: the
+    [n, 50265] logits never exist) against the plain path (logits -> goat_xent) and against torch on the CPU oracle's
+    logits: per-token loss, gradient of the hidden states, of the tied 50265 x 768 weight and of the vocabulary bias."""
+    from vln_goat_b200 import goat_blocks as G, runtime
+    from vln_goat_b200.config import GoatConfig
+    torch.manual_seed(3)
+    cfg = GoatConfig()
+    head = G.BertOnlyMLMHead(cfg)
+    shapes = {k: tuple(v.shape) for k, v in head.state_dict().items()}
+    head.load_state_dict(O.seeded_params(shapes, seed=33))
+    head = head.cuda().eval()
+    n = 37
+    x = torch.randn(n, 768)
+    labels = torch.randint(0, 50265, (n,))
+    labels[5] = -1
+    labels[11] = 50264
+    labels[12] = 0
+    w = torch.rand(n)
+    outs = []
+    for fused in (True, False):
+        head.zero_grad()
+        xc = x.clone().cuda().requires_grad_(True)
+        with runtime.compute(dtype):
+            if fused:
+                loss = head.loss(xc, labels.cuda(), ignore_index=-1)
+            else:
+                loss = G.cross_entropy(head(xc), labels.cuda(), ignore_index=-1)
+            (loss * w.cuda()).sum().backward()
+        outs.append((loss.detach().cpu(), xc.grad.cpu(), head.predictions.decoder.weight.grad.cpu().clone(),
+                     head.predictions.bias.grad.cpu().clone()))
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    for a, b, name in zip(outs[0], outs[1], ("loss", "dx", "dW", "dbias")):
+        scale = max(1e-6, b.abs().max().item()) if name != "loss" else max(1.0, b.abs().max().item())
+        assert (a - b).abs().max().item() <= tol * scale, (name, (a - b).abs().max().item(), scale)
+    assert outs[0][0][5].item() == 0.0
+    # against torch autograd on the oracle's fp32 logits
+    P = {k: v.float().cpu() for k, v in head.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    h = O.head_transform(P, "predictions.transform.", xr, cfg.layer_norm_eps)
+    logits = O.linear(h, P["predictions.decoder.weight"], P["predictions.bias"])
+    ref = F.cross_entropy(logits, labels, reduction="none", ignore_index=-1)
+    (ref * w).sum().backward()
+    ftol = 2e-5 if dtype == torch.float32 else 2e-3
+    assert _rel(outs[0][0], ref.detach()) < ftol
+    assert (outs[0][1] - xr.grad).abs().max().item() <= (ftol * 5) * max(1e-6, xr.grad.abs().max().item())

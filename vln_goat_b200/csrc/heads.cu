@@ -295,6 +295,55 @@ xent_bwd_kernel(const float* __restrict__ dloss, const float* __restrict__ logit
 }
 
 // ---------------------------------------------------------------------------------------------
+// chunked cross-entropy over a wide class axis (the 50265-word vocabulary of the MLM head): the logits exist only one
+// column chunk [c0, c0 + Nc) at a time.  forward keeps running (max, sum exp, picked logit) per row across the chunks;
+// backward turns a recomputed logits chunk into the 16-bit gradient operand of the dgrad / wgrad GEMMs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(XENT_THREADS)
+xent_chunk_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels, int Nc,
+                      long long c0, int first, float* __restrict__ run_m, float* __restrict__ run_l,
+                      float* __restrict__ picked) {
+  __shared__ float red[XENT_THREADS / 32];
+  const int i = blockIdx.x;
+  const float* row = logits + (size_t)i * ld;
+  float m = -CUDART_INF_F;
+  for (int j = threadIdx.x; j < Nc; j += XENT_THREADS) m = fmaxf(m, row[j]);
+  m = block_max(m, red);
+  const float m_old = first ? -CUDART_INF_F : run_m[i];
+  const float m_new = fmaxf(m, m_old);
+  float l = 0.f;
+  for (int j = threadIdx.x; j < Nc; j += XENT_THREADS) l += __expf(row[j] - m_new);
+  l = block_sum(l, red);
+  if (threadIdx.x == 0) {
+    const float l_old = first ? 0.f : run_l[i];
+    run_l[i] = l + ((m_old == -CUDART_INF_F) ? 0.f : l_old * __expf(m_old - m_new));
+    run_m[i] = m_new;
+    const long long lab = labels[i] - c0;
+    if (first) picked[i] = 0.f;
+    if (lab >= 0 && lab < Nc) picked[i] = row[lab];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(XENT_THREADS)
+xent_chunk_bwd_kernel(const float* __restrict__ dloss, const float* __restrict__ logits, long long ld,
+                      const long long* __restrict__ labels, const float* __restrict__ lse, int Nc, long long c0,
+                      long long ignore_index, long long n_classes, T* __restrict__ out, long long ldo) {
+  const int i = blockIdx.x;
+  const long long lab = labels[i];
+  const float g = (lab == ignore_index || lab < 0 || lab >= n_classes) ? 0.f : dloss[i];
+  const float e = lse[i];
+  const float* row = logits + (size_t)i * ld;
+  T* orow = out + (size_t)i * ldo;
+  const long long hit = lab - c0;
+  for (int j = threadIdx.x + blockIdx.y * XENT_THREADS; j < Nc; j += XENT_THREADS * gridDim.y) {
+    float d = 0.f;
+    if (g != 0.f) d = g * (__expf(row[j] - e) - (j == hit ? 1.f : 0.f));
+    orow[j] = from_f<T>(d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // gather-and-reduce: out[r,:] = scale_r * sum_{k < K, idx[r,k] >= 0} src[idx[r,k], :]
 //   scale_r = 1 (sum) or 1 / #valid (mean; 0 valid entries -> zeros).
 // ---------------------------------------------------------------------------------------------
@@ -584,6 +633,41 @@ int goat_sprel_bwd(const float* dout, const float* d, float* dw, float* db, long
   if (n <= 0) return GOAT_OK;
   long long want = (n + 256 * 8 - 1) / (256 * 8);
   sprel_bwd_kernel<<<(int)(want > 148 ? 148 : want), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, d, dw, db, n);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+int goat_xent_chunk_fwd(const float* logits, long long ld, const long long* labels, int M, int Nc, long long c0, int first,
+                        float* run_max, float* run_sum, float* picked, goat_stream_t stream) {
+  GOAT_CHECK(logits && labels && run_max && run_sum && picked, "goat_xent_chunk_fwd: null argument");
+  GOAT_CHECK(Nc >= 1 && ld >= Nc, "goat_xent_chunk_fwd: bad chunk width / leading dimension");
+  if (M <= 0) return GOAT_OK;
+  xent_chunk_fwd_kernel<<<M, XENT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, labels, Nc, c0, first,
+                                                                                        run_max, run_sum, picked);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+int goat_xent_chunk_bwd(const float* dloss, const float* logits, long long ld, const long long* labels, const float* lse,
+                        int M, int Nc, long long c0, long long ignore_index, long long n_classes, void* out, int out_dtype,
+                        long long ldo, goat_stream_t stream) {
+  GOAT_CHECK(dloss && logits && labels && lse && out, "goat_xent_chunk_bwd: null argument");
+  GOAT_CHECK(out_dtype == GOAT_F32 || out_dtype == GOAT_F16 || out_dtype == GOAT_BF16, "goat_xent_chunk_bwd: bad out dtype");
+  GOAT_CHECK(Nc >= 1 && ld >= Nc && ldo >= Nc, "goat_xent_chunk_bwd: bad chunk width / leading dimension");
+  if (M <= 0) return GOAT_OK;
+  int gy = (Nc + XENT_THREADS * 8 - 1) / (XENT_THREADS * 8);
+  if (gy < 1) gy = 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(M, gy);
+  if (out_dtype == GOAT_F32)
+    xent_chunk_bwd_kernel<float><<<grid, XENT_THREADS, 0, st>>>(dloss, logits, ld, labels, lse, Nc, c0, ignore_index, n_classes,
+                                                                 (float*)out, ldo);
+  else if (out_dtype == GOAT_F16)
+    xent_chunk_bwd_kernel<__half><<<grid, XENT_THREADS, 0, st>>>(dloss, logits, ld, labels, lse, Nc, c0, ignore_index, n_classes,
+                                                                  (__half*)out, ldo);
+  else
+    xent_chunk_bwd_kernel<__nv_bfloat16><<<grid, XENT_THREADS, 0, st>>>(dloss, logits, ld, labels, lse, Nc, c0, ignore_index,
+                                                                         n_classes, (__nv_bfloat16*)out, ldo);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

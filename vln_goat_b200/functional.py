@@ -604,6 +604,69 @@ class XentFn(torch.autograd.Function):
         return ops.xent_bwd(dloss.contiguous(), logits, labels, lse, ctx.ignore_index, out=out), None, None
 
 
+class VocabXentFn(torch.autograd.Function):
+    """cross_entropy(h W^T + b, labels) per row WITHOUT materialising the [n, vocab] logits (the reference
+    writes them as fp32 and reads them back three times, P/model/Bert_backbone.py:826 + P/model/pretrain_goat.py:209-224).
+    The class axis is walked in chunks of ``CHUNK`` columns: forward = chunk GEMM (tcgen05, fp32 out into ONE reused,
+    L2-resident buffer) + a running (max, sum exp, picked logit) update; backward recomputes each chunk's logits, turns
+    them into the 16-bit gradient chunk, and feeds the dgrad (accumulated over chunks) / wgrad / bias-gradient kernels."""
+
+    CHUNK = 6144      # 24 tiles of 256 columns x 3 row tiles of a 640-row batch = 72 pair tiles: one wave of the 74 pairs
+
+    @staticmethod
+    def forward(ctx, h32, W, b, labels, ignore_index, W_c, cdt):
+        n, V = h32.shape[0], W.shape[0]
+        hc = _c(h32.contiguous(), None, cdt)
+        labels = labels.contiguous()
+        dev = h32.device
+        m = torch.empty(n, device=dev, dtype=torch.float32)
+        l = torch.empty(n, device=dev, dtype=torch.float32)
+        picked = torch.empty(n, device=dev, dtype=torch.float32)
+        C_ = min(VocabXentFn.CHUNK, _pad8(V))
+        buf = torch.empty((n, C_), device=dev, dtype=torch.float32)
+        for c0 in range(0, V, C_):
+            nc = min(C_, V - c0)
+            lg = ops.gemm(hc, W_c[c0:c0 + nc], bias=None if b is None else b.detach()[c0:c0 + nc], out=buf[:, :nc],
+                          out_dtype=torch.float32)
+            ops.xent_chunk_fwd(lg, labels, c0, c0 == 0, m, l, picked)
+        lse = m + torch.log(l)
+        valid = labels != ignore_index
+        loss = torch.where(valid, lse - picked, torch.zeros_like(lse))
+        ctx.ignore_index, ctx.cdt, ctx.chunk = ignore_index, cdt, C_
+        ctx.params = (W, b)
+        ctx.save_for_backward(hc, W_c, labels, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        hc, W_c, labels, lse = ctx.saved_tensors
+        W, b = ctx.params
+        cdt, C_ = ctx.cdt, ctx.chunk
+        n, V = hc.shape[0], W.shape[0]
+        dev = hc.device
+        dloss = dloss.contiguous()
+        buf = torch.empty((n, C_), device=dev, dtype=torch.float32)
+        d16 = torch.empty((n, C_), device=dev, dtype=cdt)
+        dh = torch.zeros((n, hc.shape[1]), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        gW = getattr(W, "_goat_grad", None)
+        gb = getattr(b, "_goat_grad", None) if b is not None else None
+        dW = None if gW is not None else torch.zeros(W.shape, device=dev, dtype=torch.float32)
+        db = None if (gb is not None or b is None) else torch.zeros(b.shape, device=dev, dtype=torch.float32)
+        for c0 in range(0, V, C_):
+            nc = min(C_, V - c0)
+            lg = ops.gemm(hc, W_c[c0:c0 + nc], bias=None if b is None else b.detach()[c0:c0 + nc], out=buf[:, :nc],
+                          out_dtype=torch.float32)
+            dl = d16[:, :nc]
+            ops.xent_chunk_bwd(dloss, lg, labels, lse, c0, ctx.ignore_index, V, dl)
+            if dh is not None:
+                ops.gemm(dl, W_c[c0:c0 + nc], b_mn=True, out=dh, accumulate=True)            # dh += dlogits_c W_c
+            ops.gemm(dl, hc, a_mn=True, b_mn=True, out=(gW if gW is not None else dW)[c0:c0 + nc], accumulate=True)
+            if b is not None:
+                ops.colsum(dl, out=(gb if gb is not None else db)[c0:c0 + nc], accumulate=True)
+        _mark((W, b))
+        return dh, dW, db, None, None, None, None
+
+
 class SegmentReduceFn(torch.autograd.Function):
     """out[r] = sum / mean over k of src[idx[r,k]] (idx -1 = empty)."""
 

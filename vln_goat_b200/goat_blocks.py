@@ -136,6 +136,14 @@ class BertLMPredictionHead(nn.Module):
         return y.view(shp[:-1] + (self.decoder.weight.shape[0],))
 
 
+    def loss(self, hidden_states, labels, ignore_index=-1):
+        """cross_entropy(self(hidden_states), labels, reduction='none') without the [n, vocab] logits in memory"""
+        h = self.transform(hidden_states)
+        cdt = runtime.compute_dtype()
+        return Fn.VocabXentFn.apply(h.reshape(-1, h.shape[-1]), self.decoder.weight, self.bias, labels.reshape(-1),
+                                    ignore_index, runtime.wc(self.decoder.weight, cdt), cdt)
+
+
 class BertOnlyMLMHead(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -143,6 +151,9 @@ class BertOnlyMLMHead(nn.Module):
 
     def forward(self, sequence_output):
         return self.predictions(sequence_output)
+
+    def loss(self, sequence_output, labels, ignore_index=-1):
+        return self.predictions.loss(sequence_output, labels, ignore_index)
 
 
 def cross_entropy(logits, labels, ignore_index=-100):

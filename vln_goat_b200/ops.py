@@ -414,6 +414,27 @@ def xent_bwd(dloss, logits, labels, lse, ignore_index=-100, out=None, accumulate
     return out
 
 
+def xent_chunk_fwd(logits, labels, c0, first, run_max, run_sum, picked):
+    """one column chunk [c0, c0+Nc) of the logits (fp32 [M,Nc], unit inner stride): update the running row statistics"""
+    _req_cuda(logits, labels, run_max, run_sum, picked)
+    M, Nc = logits.shape
+    if logits.dtype != torch.float32 or logits.stride(1) != 1:
+        raise ValueError("xent_chunk_fwd: logits must be fp32 with unit inner stride")
+    _lib.check(_lib.lib().goat_xent_chunk_fwd(_p(logits), logits.stride(0), _p(labels), M, Nc, int(c0), int(first),
+                                              _p(run_max), _p(run_sum), _p(picked), _stream()), "goat_xent_chunk_fwd")
+    LAUNCHES[0] += 1
+
+
+def xent_chunk_bwd(dloss, logits, labels, lse, c0, ignore_index, n_classes, out):
+    """out [M,Nc] (any dtype, unit inner stride) = dloss (softmax - onehot) for the chunk starting at class c0"""
+    _req_cuda(dloss, logits, labels, lse, out)
+    M, Nc = logits.shape
+    _lib.check(_lib.lib().goat_xent_chunk_bwd(_p(dloss), _p(logits), logits.stride(0), _p(labels), _p(lse), M, Nc, int(c0),
+                                              int(ignore_index), int(n_classes), _p(out), dt(out), out.stride(0), _stream()),
+               "goat_xent_chunk_bwd")
+    LAUNCHES[0] += 1
+
+
 def segment_reduce_fwd(src, idx, mean):
     """src [R0,H] fp32, idx int32 [R,K] (-1 = empty) -> out [R,H]"""
     _req_cuda(src, idx)

@@ -238,10 +238,10 @@ class GlocalTextPathCMTPreTraining(nn.Module):
         txt_embeds = g_txt + v_txt
         H = txt_embeds.shape[-1]
         masked_output = Fn.SegmentReduceFn.apply(txt_embeds.reshape(-1, H), P["mlm_rows"], False)
-        prediction_scores = self.mlm_head(masked_output)
         if compute_loss:
-            return G.cross_entropy(prediction_scores, P["mlm_labels"], ignore_index=-1)
-        return prediction_scores
+            # chunked vocabulary projection + cross-entropy: the [n, 50265] logits never exist in memory
+            return self.mlm_head.loss(masked_output, P["mlm_labels"], ignore_index=-1)
+        return self.mlm_head(masked_output)
 
     def _fuse_weights(self, gmap_embeds, vp_embeds):
         if self.sap_fuse_linear is None:
