@@ -83,6 +83,38 @@ def test_gemm_epilogues(dtype):
     assert rel(d1[kept], (acc / 0.9)[kept.cpu()] if not acc.is_cuda else (acc / 0.9)[kept]) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(5120, 3072, 768), (2368, 2304, 768), (6912, 3072, 768)])
+def test_gemm_tail_wave_split_keeps_every_epilogue_operand_aligned(M, N, K):
+    """Shapes whose last wave of 256 x 256 tiles is mostly empty run as two launches (row tiles that fill whole waves, then
+    the remaining rows as 256 x 128 tiles; gemm_umma.cu).  The second launch must see its rows of the residual, the GELU
+    pre-activation copies and the SAME dropout mask (indexed by the global row): compare with the SIMT kernel."""
+    from vln_goat_b200 import ops
+    torch.manual_seed(M + N)
+    dtype = torch.float16
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(dtype)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(dtype)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    acc = A.double() @ W.double().t()
+    out2 = torch.empty(M, N, device=DEV, dtype=dtype)
+    out = ops.gemm(A, W, bias=bias, res=res, out_dtype=torch.float32, out2=out2, drop_p=0.1, drop_seed=4242)
+    ref = ops.gemm(A, W, bias=bias, res=res, out_dtype=torch.float32, drop_p=0.1, drop_seed=4242, force_simt=True)
+    assert rel(out, ref) < 2e-5
+    assert rel(out2, ref) < OUT_TOL[dtype]
+    mask = ops.cast(torch.ones(M, N, device=DEV), torch.float32, drop_p=0.1, drop_seed=4242) != 0
+    plain = acc + bias.double() + res.double()
+    assert rel(out[~mask], (bias.double() * 0 + res.double())[~mask]) < 2e-5     # dropped: only the residual survives
+    z = torch.empty(M, N, device=DEV, dtype=dtype)
+    h = ops.gemm(A, W, bias=bias, act=ops.ACT_GELU, aux_out=z)
+    assert rel(z, acc + bias.double()) < OUT_TOL[dtype]
+    assert rel(h, O.gelu_erf(z.double())) < OUT_TOL[dtype]
+    g = ops.gemm(A, W, act=ops.ACT_DGELU, aux_in=z)
+    zz = z.double().requires_grad_(True)
+    O.gelu_erf(zz).sum().backward()
+    assert rel(g, acc * zz.grad) < OUT_TOL[dtype]
+    del plain
+
+
 def test_dropout_mask_is_shared_by_gemm_layernorm_and_cast():
     """Hidden dropout is applied in a GEMM epilogue (forward) and regenerated by the LayerNorm backward / cast kernels
     from (seed, linear element index): all three must draw the same keep mask, at the requested rate."""

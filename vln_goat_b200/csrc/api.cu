@@ -84,6 +84,7 @@ int goat_gemm(const goat_gemm_args* a, goat_stream_t stream_) {
   ep.drop_p = a->drop_p;
   ep.drop_seed = a->drop_seed;
   ep.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(a->drop_seed_ptr);
+  ep.drop_row0 = 0;
   if (!a->force_simt && gemm_umma_eligible(*a)) {
     GOAT_CHECK(aligned16(a->out) && (!a->out2 || aligned16(a->out2)) && (!a->res || aligned16(a->res)) &&
                    (!a->aux_in || aligned16(a->aux_in)) && (!a->aux_out || aligned16(a->aux_out)) &&

@@ -205,6 +205,7 @@ struct EpiParams {
   float drop_p;          // dropout probability applied after activation, before residual (0 = off)
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_ptr;  // optional device word added to drop_seed
+  long long drop_row0;   // global row of this launch's row 0 (a GEMM split over two launches keeps ONE dropout mask)
 };
 
 __device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed, const unsigned long long* ptr) {
@@ -231,7 +232,7 @@ __device__ __forceinline__ float epi_apply(const EpiParams& ep, int m, int n, fl
   }
   if (ep.drop_p > 0.0f) {
     const bool keep = drop_keep(eff_seed(ep.drop_seed, ep.drop_seed_ptr),
-                                (unsigned long long)m * (unsigned long long)ep.ldc + n, drop_thr16(ep.drop_p));
+                                (unsigned long long)(m + ep.drop_row0) * (unsigned long long)ep.ldc + n, drop_thr16(ep.drop_p));
     v = keep ? v * (1.0f / (1.0f - ep.drop_p)) : 0.0f;
   }
   if (ep.res) v += ep.res[(size_t)m * ep.ldres + n];

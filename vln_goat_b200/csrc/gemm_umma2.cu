@@ -190,7 +190,7 @@ __device__ __forceinline__ void epi_out4(const EpiParams& ep, int m, int n, floa
     v[0] *= dgelu_fast(a.x); v[1] *= dgelu_fast(a.y); v[2] *= dgelu_fast(b.x); v[3] *= dgelu_fast(b.y);
   }
   if constexpr (MODE != EPI_T16) {
-    if (ep.drop_p > 0.0f) drop_apply4(v, seed, (unsigned long long)m * (unsigned long long)ep.ldc + n, thr16, keep);
+    if (ep.drop_p > 0.0f) drop_apply4(v, seed, (unsigned long long)(m + ep.drop_row0) * (unsigned long long)ep.ldc + n, thr16, keep);
   }
   if constexpr (MODE == EPI_RES32) {
     if (ep.res) { v[0] += pre.res[i].x; v[1] += pre.res[i].y; v[2] += pre.res[i].z; v[3] += pre.res[i].w; }
@@ -518,11 +518,20 @@ int launch2(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   sc.splits = 1;
   const int mn = sc.tiles_m * sc.tiles_n;
   if (ep.accumulate && mn < pairs) {
-    // split K so that about one wave of pair tiles exists, keeping at least 4 k-blocks (256 of K) per split
-    int want = (pairs + mn - 1) / mn;
+    // split K (at least 4 k-blocks = 256 of K per split) so that the tile count fills whole waves of the 74 pairs:
+    // cost(s) = waves(mn * s) / s in units of the unsplit tile time.  (Rounding the split count UP to "about one wave"
+    // put e.g. 9 x 9 = 81 tiles on 74 pairs: two waves for the work of 1.1.)
     int cap = sc.num_kb / 4;
     if (cap < 1) cap = 1;
-    sc.splits = want < cap ? want : cap;
+    if (cap > 32) cap = 32;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= cap; ++s) {
+      const int waves = (mn * s + pairs - 1) / pairs;
+      const double cost = (double)waves / s + 0.02 * s;    // small penalty per split: extra atomics traffic
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    sc.splits = best;
   }
   sc.kb_per_split = (sc.num_kb + sc.splits - 1) / sc.splits;
   sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
