@@ -26,6 +26,8 @@ One JSON line on rank 0:
   cpu_baseline        the CPU restatement of the same step (oracle/, torch fp32, all host cores), one step per task
   eager_b200_baseline the same restatement run eagerly on the B200 (fp32 and autocast fp16): the honest denominator
   c2          second line: BASELINE.json configs[1] (9-layer cross-encoder slice, batch 64) on the same kernels
+  c4          BASELINE.json configs[3]: 16-episode x 15-step fine-tune rollout (BACL + FACL), eager vs one captured graph
+  c5          BASELINE.json configs[4]: the same slice with 512-token instructions, batch 32, + the long-text attention core
 --impl reference times only the CPU path (the reference is pure PyTorch; /root/reference does not travel to the GPU
 box, so the committed oracle port, pinned to the reference by tests/golden, stands in for it).
 """
@@ -442,6 +444,8 @@ def run_goat(args):
             if world == 1:
                 line["eager_b200_baseline"] = eager_baseline(torch, host, dev)
                 line["c2"] = run_c2(torch, cdt, dev)
+                line["c5"] = run_c2(torch, cdt, dev, steps=20, L=512, B=32, name="C5 (RxR long-instruction stress)")
+                line["c4"] = run_c4(torch, cdt, dev)
                 if not args.no_cpu_baseline:
                     v, dt, cores, n = time_cpu(3, 0)
                     line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
@@ -698,8 +702,8 @@ def attention_roofline(torch, ops, ts, resident, cdt, step_ms):
 # ------------------------------------------------------------------------------------------------
 # second line: BASELINE.json configs[1] (the round-1 headline): 6 RobertaLayer + 3 BertCrossLayer, batch 64
 # ------------------------------------------------------------------------------------------------
-def run_c2(torch, cdt, dev, steps=60):
-    from vln_goat_b200 import engine, workloads
+def run_c2(torch, cdt, dev, steps=60, L=L, B=B, name="C2"):
+    from vln_goat_b200 import engine, ops, workloads
     from vln_goat_b200.config import GoatConfig
     torch.manual_seed(0)
     model = workloads.C2CrossEncoder(GoatConfig()).to(dev).train()
@@ -709,7 +713,7 @@ def run_c2(torch, cdt, dev, steps=60):
         return workloads.c2_loss(t, v)
     g = torch.Generator().manual_seed(5)
     batches = []
-    for _ in range(4):
+    for _ in range(2 if L > 128 else 4):
         txt = torch.randn(B, L, H, generator=g)
         vp = torch.randn(B, NQ, H, generator=g)
         vp[:, 0] = 0.0
@@ -722,18 +726,121 @@ def run_c2(torch, cdt, dev, steps=60):
     if cdt == torch.float16:
         flat.enable_loss_scale()
     ts = engine.TrainStep(flat, loss_fn, batches[0], **OPT)
+    nb = len(batches)
     for i in range(5):
-        ts.step(batches[i % 4])
+        ts.step(batches[i % nb])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        ts.step(batches[i % 4])
+        ts.step(batches[i % nb])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"workload": "C2: 6 RobertaLayer + 3 BertCrossLayer fwd+bwd+clip+AdamW (70.9 M params), batch 64, device-resident",
-            "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps, "gpu_launches_per_step": ts.launches_per_step}
+    out = {"workload": "%s: 6 RobertaLayer + 3 BertCrossLayer fwd+bwd+clip+AdamW (70.9 M params), batch %d, %d text tokens x %d "
+                       "view tokens, device-resident" % (name, B, L, NQ),
+           "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps, "gpu_launches_per_step": ts.launches_per_step}
+    if L > 128 and cdt != torch.float32:
+        # the long-instruction attention core alone (query-tiled tcgen05 kernels, attention_tc.cu): achieved HBM GB/s
+        heads = 12
+        q = torch.randn(B, L, H, device=dev).to(cdt)
+        km = torch.zeros(B, L, device=dev)
+        o, lse = ops.attn_fwd(q, q, q, heads, km, drop_p=0.1, drop_seed=3)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        f_ms = _time_graph(torch, lambda: ops.attn_fwd(q, q, q, heads, km, drop_p=0.1, drop_seed=3))
+        b_ms = _time_graph(torch, lambda: ops.attn_bwd(q, q, q, q, o, lse, heads, dq, dk, dv, km, drop_p=0.1, drop_seed=3))
+        fb = 2.0 * B * H * 4 * L + 4.0 * B * L
+        bb = 2.0 * B * H * 8 * L + 4.0 * B * L
+        pk = peaks().get("hbm_gbs") or 6650.0
+        fl = 4.0 * B * L * L * H
+        out["attention_self_%d" % L] = {
+            "fwd_us": f_ms * 1e3, "bwd_us": b_ms * 1e3, "fwd_gbs": fb / (f_ms * 1e-3) / 1e9, "bwd_gbs": bb / (b_ms * 1e-3) / 1e9,
+            "fwd_frac_of_hbm": fb / (f_ms * 1e-3) / 1e9 / pk, "bwd_frac_of_hbm": bb / (b_ms * 1e-3) / 1e9 / pk,
+            "fwd_tflops": fl / (f_ms * 1e-3) / 1e12, "bwd_tflops": 2.5 * fl / (b_ms * 1e-3) / 1e12,
+            "note": "text self-attention B%d x 12 heads x %d x %d, dropout 0.1; bytes = Q,K,V,O (+ dO,dQ,dK,dV) in 16 bit + key mask" % (B, L, L)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: fine-tune rollout, 16 parallel episodes x 15 steps, BACL + FACL on (per GPU; episodes are
+# independent, so N GPUs run N such rollouts with the same gradient exchange as the pretraining step)
+# ------------------------------------------------------------------------------------------------
+def run_c4(torch, cdt, dev, episodes=16, T=15, reps=4):
+    from vln_goat_b200 import engine, nav_model, workloads
+    from vln_goat_b200.config import GoatConfig
+    cfg = GoatConfig(layer_norm_eps=1e-5, pad_token_id=1, dataset="r2r", mode="train", obj_feat_size=0, feat_dropout=0.4,
+                     do_back_img=True, do_back_txt=True, do_front_img=True, do_front_his=True, do_front_txt=True,
+                     do_back_txt_type="type_2", do_back_img_type="type_1", do_add_method="door", use_lang2visn_attn=False,
+                     fix_lang_embedding=False, fix_pano_embedding=False, fix_local_branch=False)
+    torch.manual_seed(0)
+    model = nav_model.GlocalTextPathNavCMT(cfg).to(dev).train()
+    lang, steps, targets, mem0 = workloads.synthetic_nav_rollout(episodes, L, T, seed=7)
+    flat_in = {"mem0": mem0}
+    for k, v in lang.items():
+        flat_in["lang." + k] = v
+    for t, ((pano, nav), tgt) in enumerate(zip(steps, targets)):
+        for k, v in pano.items():
+            if torch.is_tensor(v):
+                flat_in["s%02d.p.%s" % (t, k)] = v
+        for k, v in nav.items():
+            flat_in["s%02d.n.%s" % (t, k)] = v
+        flat_in["s%02d.t" % t] = tgt
+    h2d = sum(v.numel() * v.element_size() for v in flat_in.values())
+    dev_in = {k: v.to(dev) for k, v in flat_in.items()}
+
+    def loss_fn(D):
+        lg = {k[5:]: v for k, v in D.items() if k.startswith("lang.")}
+        st, tg = [], []
+        for t in range(T):
+            pre = "s%02d." % t
+            pano = {k[len(pre) + 2:]: v for k, v in D.items() if k.startswith(pre + "p.")}
+            pano["already_dropout"] = True
+            nav = {k[len(pre) + 2:]: v for k, v in D.items() if k.startswith(pre + "n.")}
+            st.append((pano, nav))
+            tg.append(D[pre + "t"])
+        return workloads.nav_rollout_loss(model, lg, st, tg, D["mem0"])
+
+    # (a) eager autograd (how the reference's agent drives the model: one Python call per op)
+    def eager():
+        model.zero_grad(set_to_none=True)
+        loss = loss_fn(dev_in)
+        loss.backward()
+        return loss
+    for _ in range(2):
+        eager()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        eager()
+    torch.cuda.synchronize()
+    eager_ms = (time.perf_counter() - t0) / reps * 1e3
+    # (b) the same rollout as ONE captured CUDA graph (forward + backward of all 15 steps) + fused clip / AdamW
+    active = engine.active_parameters(model, loss_fn, (dev_in,))
+    flat = engine.FlatParams(model, shadow_dtype=cdt if cdt != torch.float32 else None, only=active)
+    if cdt == torch.float16:
+        flat.enable_loss_scale()
+    ts = engine.TrainStep(flat, loss_fn, dev_in, lr=1e-5, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, max_grad_norm=40.0,
+                          check_unwritten=False)
+    for _ in range(3):
+        ts.step(dev_in)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3 * reps
+    e0.record()
+    for _ in range(n):
+        loss = ts.step(dev_in)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    if not bool(torch.isfinite(loss)):
+        raise RuntimeError("non-finite rollout loss")
+    return {"workload": "C4: teacher-forced fine-tune rollout, %d episodes x %d steps (language once, panorama + navigation per "
+                        "step, BACL + FACL on, global map growing 8 -> 56 nodes), fwd + bwd + clip + AdamW, 188 M params" % (episodes, T),
+            "value": 1e3 / ms, "unit": "rollouts/s", "ms_per_rollout": ms, "ms_per_nav_step": ms / T,
+            "eager_ms_per_rollout": eager_ms, "graph_speedup_vs_eager": eager_ms / ms,
+            "gpu_launches_per_rollout": ts.launches_per_step, "h2d_bytes_per_rollout": h2d, "loss": float(loss),
+            "note": "the whole rollout (all steps, one backward) is ONE CUDA graph: with teacher forcing the observations do "
+                    "not depend on the model's outputs, so every step's inputs and logit-fusion indices are built up front"}
 
 
 def main():

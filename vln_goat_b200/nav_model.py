@@ -95,16 +95,20 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                     gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
                                     vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats=None, front_gmap_feats=None,
-                                    flops_count=False):
+                                    flops_count=False, fuse_idx=None):
+        """fuse_idx: optional int32 [B,G,K] device tensor from goat_blocks.build_fusion_index, built by the caller on the
+        host (then ``gmap_vpids`` / ``vp_cand_vpids`` are not needed and the step has no host synchronisation: a whole
+        teacher-forced rollout can be captured in one CUDA graph)."""
         with M.kv_cache_scope(self._kv_cache):
             return self._navigation_step(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                          gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
                                          vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats,
-                                         front_gmap_feats, flops_count)
+                                         front_gmap_feats, flops_count, fuse_idx)
 
     def _navigation_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                          gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
-                         vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats, front_gmap_feats, flops_count):
+                         vp_nav_masks, vp_obj_masks, vp_cand_vpids, front_vp_feats, front_gmap_feats, flops_count,
+                         fuse_idx=None):
         ge, le = self.global_encoder, self.local_encoder
         # global branch
         gmap_embeds = gmap_img_embeds + ge.step_embed(gmap_step_ids) + G._pos_embed(ge.gmap_pos_embeddings, gmap_pos_fts)
@@ -132,8 +136,9 @@ class GlocalTextPathNavCMT(nn.Module):
             fused_logits = global_logits.clone()
             fused_logits[:, 0] = fused_logits[:, 0] + local_logits[:, 0]
         else:
-            idx = G.build_fusion_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, local_logits.size(1), 2, 2)
-            fused_logits = G.fuse_logits(global_logits, local_logits, idx.to(global_logits.device))
+            if fuse_idx is None:
+                fuse_idx = G.build_fusion_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, local_logits.size(1), 2, 2)
+            fused_logits = G.fuse_logits(global_logits, local_logits, fuse_idx.to(global_logits.device))
         # per-step history token
         cls = torch.cat((self.gmap_pooler(gmap_embeds, location=0), self.vp_pooler(vp_embeds, location=0),
                          self.txt_pooler(txt_embeds, location=0)), dim=-1)
@@ -160,7 +165,7 @@ class GlocalTextPathNavCMT(nn.Module):
                 batch["gmap_pos_fts"], batch["gmap_masks"], batch["gmap_pair_dists"], batch["gmap_visited_masks"],
                 batch["gmap_vpids"], batch["vp_img_embeds"], batch["vp_pos_fts"], batch["vp_masks"], batch["vp_nav_masks"],
                 batch["vp_obj_masks"], batch["vp_cand_vpids"], batch["front_vp_feats"], batch["front_gmap_feats"],
-                flops_count=batch["flops_count"])
+                flops_count=batch["flops_count"], fuse_idx=batch["fuse_idx"])
         if mode == "instr_zdict_update":
             return self.forward_text(batch["z_txt"], batch["z_txt_mask"],
                                      instr_z_direction_features=batch["instr_z_direction_features"],

@@ -166,3 +166,118 @@ def synthetic_pretrain_batch(B=64, L=80, seed=0, views=36, max_steps=5, H=768):
 
 
 PRETRAIN_TASKS = ("mlm", "sap", "cfp")
+
+
+# --------------------------------------------------------------------------------------
+# C4: a teacher-forced fine-tune rollout (language once, then panorama + navigation per step; BACL + FACL inputs) with
+# the per-step layouts of M/r2r/agent.py:86-304 / M/utils/efficiency_count.py:16-109
+# --------------------------------------------------------------------------------------
+def synthetic_nav_rollout(B=16, L=80, T=15, seed=0, views=36, H=768):
+    """-> (language batch, [(panorama batch, navigation batch)] x T, [target node index] x T), host tensors.
+    The global map grows with the step (2 + visited + frontier nodes, padded to a multiple of 8); the logit-fusion
+    index of every step is built here on the host (goat_blocks.build_fusion_index), so the navigation batches carry no
+    Python lists and a whole rollout is shape-static."""
+    from . import goat_blocks as G
+    g = torch.Generator().manual_seed(seed)
+    txt_lens = torch.randint(L // 2, L + 1, (B,), generator=g)
+    txt_lens[0] = L
+    txt_ids = torch.ones(B, L, dtype=torch.int64)
+    for i in range(B):
+        n = int(txt_lens[i])
+        txt_ids[i, :n] = torch.randint(3, 50000, (n,), generator=g)
+    txt_masks = torch.arange(L)[None, :] < txt_lens[:, None]
+
+    def pz(n):
+        p = torch.rand(B, n, 1, generator=g, dtype=torch.float64)
+        return p / p.sum(1, keepdim=True)
+    lang = {"txt_ids": txt_ids, "txt_masks": txt_masks,
+            "instr_z_direction_features": torch.randn(B, 35, H, generator=g), "instr_z_direction_pzs": pz(35),
+            "instr_z_landmark_features": torch.randn(B, 39, H, generator=g), "instr_z_landmark_pzs": pz(39),
+            "front_txt_feats": torch.tanh(torch.randn(B, 24, H, generator=g))}
+    front_vp = torch.tanh(torch.randn(B, 24, H, generator=g))
+    front_gmap = torch.tanh(torch.randn(B, 24, H, generator=g))
+    z_img, z_pz = torch.randn(B, 50, H, generator=g), pz(50)
+    steps, targets = [], []
+    for t in range(T):
+        nvis = t + 1
+        ncand = [3 + (i + t) % 4 for i in range(B)]
+        unv = [min(2 + 2 * t + i % 3, 40) for i in range(B)]
+        gl = [2 + nvis + u for u in unv]
+        Gp = (max(gl) + 7) // 8 * 8
+        feats = torch.randn(B, views, H, generator=g)
+        loc = _loc_fts(B * views, g).view(B, views, 7)
+        nav_types = torch.zeros(B, views, dtype=torch.int64)
+        view_lens = torch.full((B,), views, dtype=torch.int64)
+        pano = {"view_img_fts": feats, "loc_fts": loc, "nav_types": nav_types, "view_lens": view_lens,
+                "z_img_features": z_img, "z_img_pzs": z_pz, "already_dropout": True}
+        gmap_vpids, cand_vpids = [], []
+        visited_masks = torch.zeros(B, Gp, dtype=torch.bool)
+        step_ids = torch.zeros(B, Gp, dtype=torch.int64)
+        pos = torch.zeros(B, Gp, 7)
+        pair = torch.zeros(B, Gp, Gp)
+        tgt = torch.zeros(B, dtype=torch.int64)
+        for i in range(B):
+            nav_types[i, :ncand[i]] = 1
+            vis = ["n%d_p%d" % (i, k) for k in range(nvis)]
+            front = ["n%d_f%d" % (i, k) for k in range(unv[i])]
+            cands = [vis[0]] + front[:ncand[i] - 1]            # candidate 0 leads back to a visited node
+            cand_vpids.append([None, None] + cands)
+            gmap_vpids.append([None, None] + vis + front)
+            visited_masks[i, 1:2 + nvis] = True
+            step_ids[i, 2:2 + nvis] = torch.arange(1, nvis + 1)
+            p = _loc_fts(gl[i], g)
+            p[:, 4:] = torch.rand(gl[i], 3, generator=g)
+            pos[i, :gl[i]] = p
+            d = torch.rand(gl[i], gl[i], generator=g) * 10
+            d = (d + d.t()) / 2
+            d.fill_diagonal_(0)
+            d[:2, :] = 0
+            d[:, :2] = 0
+            pair[i, :gl[i], :gl[i]] = d
+            tgt[i] = 0 if (i + t) % 5 == 4 else 2 + nvis + (i % max(1, min(ncand[i] - 1, unv[i])))
+        gmap_lens = torch.tensor(gl)
+        gmap_masks = torch.arange(Gp)[None, :] < gmap_lens[:, None]
+        gmap_masks[:, 1] = False
+        gmap_img = torch.randn(B, Gp, H, generator=g) * 0.5
+        gmap_img[:, 0] = 0
+        gmap_img = gmap_img * (torch.arange(Gp)[None, :, None] < gmap_lens[:, None, None])
+        vp_pos = torch.zeros(B, views + 2, 14)
+        for i in range(B):
+            vp_pos[i, :, :7] = _loc_fts(1, g)
+            vp_pos[i, 2:2 + ncand[i], 7:] = _loc_fts(ncand[i], g)
+        fuse_idx = G.build_fusion_index(gmap_vpids, visited_masks, cand_vpids, views + 2, 2, 2)
+        if fuse_idx.shape[1] < Gp:
+            fuse_idx = torch.cat([fuse_idx, fuse_idx.new_full((B, Gp - fuse_idx.shape[1], fuse_idx.shape[2]), -1)], 1)
+        nav = {"txt_masks": txt_masks, "gmap_img_embeds": gmap_img, "gmap_step_ids": step_ids, "gmap_pos_fts": pos,
+               "gmap_masks": gmap_masks, "gmap_pair_dists": pair, "gmap_visited_masks": visited_masks, "vp_pos_fts": vp_pos,
+               "vp_masks": torch.arange(views + 2)[None, :] < (view_lens + 2)[:, None],
+               "vp_nav_masks": torch.cat([torch.ones(B, 1, dtype=torch.bool), torch.zeros(B, 1, dtype=torch.bool),
+                                          nav_types == 1], 1),
+               "front_vp_feats": front_vp, "front_gmap_feats": front_gmap, "fuse_idx": fuse_idx.contiguous()}
+        steps.append((pano, nav))
+        targets.append(tgt)
+    mem0 = torch.randn(B, H, generator=g) * 0.5
+    return lang, steps, targets, mem0
+
+
+def nav_rollout_loss(model, lang, steps, targets, mem0):
+    """language once, then panorama + navigation per step with the [MEM] token chained through cls_embeds
+    (M/r2r/agent.py:515-592), teacher-forced cross-entropy summed over the steps and averaged over the episodes."""
+    from collections import defaultdict
+    dd = lambda d: defaultdict(lambda: None, d)
+    txt = model("language", dd(lang))
+    loss = 0.0
+    mem = mem0
+    B = mem0.shape[0]
+    for (pano, nav), tgt in zip(steps, targets):
+        pe, pm, pf = model("panorama", dd(pano))
+        navb = dict(nav)
+        navb["txt_embeds"] = txt
+        navb["vp_img_embeds"] = torch.cat([torch.zeros_like(pe[:, :1]), mem.unsqueeze(1), pe], 1)
+        gi = navb["gmap_img_embeds"]
+        navb["gmap_img_embeds"] = torch.cat([gi[:, :1], mem.unsqueeze(1), gi[:, 2:]], 1)     # gmap row 1 = [MEM] (agent.py:175)
+        outs = model("navigation", dd(navb))
+        mem = outs["cls_embeds"]
+        from . import goat_blocks as G
+        loss = loss + G.cross_entropy(outs["fused_logits"], tgt).sum()
+    return loss / B
