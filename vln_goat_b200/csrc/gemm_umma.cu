@@ -446,46 +446,6 @@ int gemm_umma(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream)
       const int tiles256 = ((a.M + 255) / 256) * ((a.N + 255) / 256);
       bn = (a.N >= 256 && (ep.accumulate || tiles256 >= 40)) ? 256 : 128;
     }
-    // Tail-wave split (non-transposed A, no split-K): T tiles of 256 x 256 on 74 pairs run ceil(T / 74) waves, and every
-    // text-tower shape (20 row tiles x {9, 12} column tiles) wastes most of its last wave.  Give the first launch the row
-    // tiles that fill whole waves and run the remaining rows as 256 x 128 tiles in a second launch (half-duration
-    // waves); the two launches write disjoint rows and overlap through programmatic dependent launch.
-    static const int tail_split = env_int("GOAT_GEMM_TAIL_SPLIT", 1);
-    if (tail_split && bn == 256 && !ep.accumulate && !a.a_mn_major && a.N >= 512) {
-      const int pairs = num_sms() / 2;
-      const int tm = (a.M + 255) / 256, tn = (a.N + 255) / 256, tn128 = (a.N + 127) / 128;
-      const int T = tm * tn;
-      const int waves_now = (T + pairs - 1) / pairs;
-      int best_m = 0;
-      double best = (double)waves_now;
-      for (int w = 1; w < waves_now; ++w) {
-        const int m_full = (w * pairs) / tn;                 // row tiles whose 256-wide tiles fit in w waves
-        if (m_full <= 0 || m_full >= tm) continue;
-        const int rest = (tm - m_full) * tn128;
-        const double cost = (double)(((m_full * tn) + pairs - 1) / pairs) + 0.5 * ((rest + pairs - 1) / pairs) + 0.08;
-        if (cost < best - 1e-9) { best = cost; best_m = m_full; }
-      }
-      if (best_m > 0) {
-        goat_gemm_args a1 = a, a2 = a;
-        EpiParams e2 = ep;
-        const long long rows = (long long)best_m * 256;
-        a1.M = (int)rows;
-        a2.M = a.M - (int)rows;
-        const long long es = 2;    // 16-bit operands
-        a2.A = reinterpret_cast<const char*>(a.A) + rows * a.lda * es;
-        const long long os = ep.out_f32 ? 4 : 2;
-        e2.out = reinterpret_cast<char*>(ep.out) + rows * ep.ldc * os;
-        if (ep.res) e2.res = ep.res + rows * ep.ldres;
-        if (ep.out2) e2.out2 = reinterpret_cast<char*>(ep.out2) + rows * ep.ldc2 * es;
-        if (ep.aux_in) e2.aux_in = reinterpret_cast<const char*>(ep.aux_in) + rows * ep.ldaux * es;
-        if (ep.aux_out) e2.aux_out = reinterpret_cast<char*>(ep.aux_out) + rows * ep.ldaux * es;
-        // dropout masks are indexed by the GLOBAL element index m * ldc + n: shift the seed-independent index base
-        e2.drop_row0 = ep.drop_row0 + rows;
-        int rc = gemm_umma2(a1, ep, 256, stream);
-        if (rc) return rc;
-        return gemm_umma2(a2, e2, 128, stream);
-      }
-    }
     return gemm_umma2(a, ep, bn, stream);
   }
   if (a.dtype == GOAT_F16) return dispatch<__half>(a, ep, stream);
