@@ -296,6 +296,9 @@ int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H,
  *   (y > 0, 1 - y^2) and the stored pre-activation (ref_dtype) for GELU.  act: GOAT_ACT_RELU / _TANH / _GELU / _NONE. */
 int goat_act_grad(const float* dy, const void* ref, int ref_dtype, int act, void* out, int out_dtype, long long n,
                   goat_stream_t stream);
+/* out[i] = act(x[i]) in fp32 (exact erf GELU): the head transforms keep their fp32 pre-activation -- applying GELU in a
+ * 16-bit GEMM epilogue would round the pre-activation to 16 bits first, which costs these fp32-out heads ~1e-3. */
+int goat_act_fwd(const float* x, int act, float* out, long long n, goat_stream_t stream);
 
 /* Spatial-relation bias of the global-map self-attention: sprel_linear = nn.Linear(1, 1) applied to every pairwise
  * distance (P/model/vilmodel_goat.py:499-501, M/models/vilmodel_GOAT.py:473-476): out[i] = d[i] * w[0] + b[0].

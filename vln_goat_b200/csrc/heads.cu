@@ -419,6 +419,13 @@ __global__ void act_grad_kernel(const float* __restrict__ dy, const R* __restric
   }
 }
 
+__global__ void act_fwd_kernel(const float* __restrict__ x, int act, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = act == GOAT_ACT_GELU ? gelu_erf(v) : act == GOAT_ACT_RELU ? fmaxf(v, 0.f) : act == GOAT_ACT_TANH ? tanhf(v) : v;
+  }
+}
+
 template <typename R>
 int act_grad_launch(const float* dy, const void* ref, int act, void* out, int od, long long n, cudaStream_t st) {
   long long want = (n + 255) / 256;
@@ -617,6 +624,17 @@ int goat_act_grad(const float* dy, const void* ref, int ref_dtype, int act, void
   if (ref_dtype == GOAT_F16) return act_grad_launch<__half>(dy, ref, act, out, out_dtype, n, st);
   if (ref_dtype == GOAT_BF16) return act_grad_launch<__nv_bfloat16>(dy, ref, act, out, out_dtype, n, st);
   GOAT_CHECK(false, "goat_act_grad: bad ref dtype");
+}
+
+int goat_act_fwd(const float* x, int act, float* out, long long n, goat_stream_t stream) {
+  GOAT_CHECK(x && out, "goat_act_fwd: null argument");
+  GOAT_CHECK(act == GOAT_ACT_NONE || act == GOAT_ACT_RELU || act == GOAT_ACT_TANH || act == GOAT_ACT_GELU,
+             "goat_act_fwd: bad act %d", act);
+  if (n <= 0) return GOAT_OK;
+  long long want = (n + 255) / 256;
+  act_fwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, act, out, n);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
 }
 
 int goat_sprel_fwd(const float* d, const float* w, const float* b, float* out, long long n, goat_stream_t stream) {

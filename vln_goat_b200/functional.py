@@ -429,12 +429,17 @@ class LinearFn(torch.autograd.Function):
         xc = _c(x32, x16, cdt)
         M, N = xc.shape[0], W.shape[0]
         aux = None
-        if act == ops.ACT_GELU:
-            aux = torch.empty((M, N), device=xc.device, dtype=cdt)
         out = None
         if N % 8 != 0 and N >= 256 and cdt != torch.float32:
             out = torch.empty((M, _pad8(N)), device=xc.device, dtype=torch.float32)[:, :N]
-        y = ops.gemm(xc, W_c, bias=b, act=act, aux_out=aux, out=out, out_dtype=torch.float32)
+        if act == ops.ACT_GELU:
+            # fp32 pre-activation kept for backward, exact erf GELU on it: a fused 16-bit epilogue would round the
+            # pre-activation to 16 bits before the GELU (fine inside an FFN, whose output is 16-bit anyway; a visible
+            # error for these fp32-out head transforms)
+            aux = ops.gemm(xc, W_c, bias=b, out_dtype=torch.float32)
+            y = ops.act_fwd(aux, act)
+        else:
+            y = ops.gemm(xc, W_c, bias=b, act=act, aux_out=aux, out=out, out_dtype=torch.float32)
         ctx.act, ctx.cdt = act, cdt
         ctx.params = (W, b)
         ctx.has_bias = b is not None

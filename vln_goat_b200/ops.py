@@ -482,6 +482,16 @@ def act_grad(dy, ref, act, out_dtype):
     return out
 
 
+def act_fwd(x, act):
+    """fp32 contiguous -> act(x) fp32 (exact erf GELU / ReLU / tanh)"""
+    _req_cuda(x)
+    _f32c(x, "x")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().goat_act_fwd(_p(x), int(act), _p(out), x.numel(), _stream()), "goat_act_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
 def sprel_fwd(d, w, b):
     """d fp32 (any shape, contiguous), w / b fp32 one element each -> d * w + b"""
     _req_cuda(d, w, b)
