@@ -11,11 +11,12 @@
 //               then the epilogue (O / l, or dV, dK, dQ) straight from TMEM to global memory
 //
 // forward : O = softmax(scale Q K^T + kmask + bias) V, lse saved
-// backward: P from lse;  delta_r = sum_k P~ dP  (= sum_d dO O, no O / dO re-read);  dS = P (dP~ - delta);
+// backward: P from lse;  delta_r = sum_d dO O (= sum_k P~ dP; computed up front, under the score MMAs);  dS = P~ dP - P delta;
 //           dV = P~^T dO, dK = scale dS^T Q, dQ = scale dS K            (P~ = dropout-masked, rescaled P)
 // TMEM: forward  O [0,64) | S [64,192);   backward dV [0,64) | dK [64,128) | dQ [128,192) | S [192,320) | dP [320,448).
 // Every contraction is a tcgen05.mma with M = 128; operand layouts / descriptors are those of attention_tc.cu.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,7 +30,6 @@ namespace {
 constexpr int P_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 compute
 constexpr int P_COMPUTE = 256;
 constexpr int TILE = 128 * 128;      // bytes of a [128 rows][64 x 2 B] tile
-constexpr int F_STAGES = 3;
 constexpr int B_STAGES = 2;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -143,10 +143,14 @@ __device__ __forceinline__ float load_kml(const PArgs& p, int b, int key) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int F_SMEM = F_STAGES * 3 * TILE + 2 * TILE + 128 + (2 * 128 + 2 * 128 + 2 * 128) * 4 + 1024;
+// Two configurations: <3 stages, 1 CTA per SM> (item i+1, i+2 prefetched under item i) and <1 stage, 2 CTAs per SM>
+// (84 KB each, 256 TMEM columns each): two independent item chains per SM hide each other's TMA -> MMA -> softmax -> MMA
+// -> store latency, which is what bounds these 37..80-row items (ncu: one chain in flight, issue slots 25 % busy).
+template <int STAGES>
+constexpr int f_smem() { return STAGES * 3 * TILE + 2 * TILE + 128 + (2 * 128 + 2 * 128 + 2 * 128) * 4 + 1024; }
 
-template <typename T>
-__global__ void __launch_bounds__(P_THREADS, 1)
+template <typename T, int F_STAGES, int MINB>
+__global__ void __launch_bounds__(P_THREADS, MINB)
 attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, PArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -457,52 +461,61 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       const float* brow = p.bias ? p.bias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
       float* dbrow = p.dbias ? p.dbias + ((long long)b * p.Nq + (rv ? r : 0)) * p.Nk : nullptr;
+      // delta_r = sum_d dO[r,d] O[r,d] (= sum_k P~ dP): each of the row's two threads takes 32 of the 64 channels -- dO from the
+      // staged tile, O from global memory -- BEFORE waiting for the score MMAs, so this overlaps them; with delta in hand
+      // one pass over the scores produces P~ and dS (no probability arrays held across a barrier, no spills)
+      {
+        const int s = i % B_STAGES;
+        mbar_wait(&full_bar[s], ((uint32_t)(i / B_STAGES)) & 1);
+        float part = 0.f;
+        if (rv) {
+          uint8_t* sdO_t = base + s * 4 * TILE + TILE;
+          const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.O) + (long long)b * p.sbo +
+                                                           (long long)r * p.ldo + h * 64 + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 g = *reinterpret_cast<const uint4*>(sw_chunk(sdO_t, r, ch * 4 + q));
+            const uint4 o = __ldg(po + q);
+            float2 x, y;
+            x = unpack2<T>(o.x); y = unpack2<T>(g.x); part += x.x * y.x + x.y * y.y;
+            x = unpack2<T>(o.y); y = unpack2<T>(g.y); part += x.x * y.x + x.y * y.y;
+            x = unpack2<T>(o.z); y = unpack2<T>(g.z); part += x.x * y.x + x.y * y.y;
+            x = unpack2<T>(o.w); y = unpack2<T>(g.w); part += x.x * y.x + x.y * y.y;
+          }
+        }
+        xd[ch * 128 + r] = part;
+      }
+      compute_bar();
+      const float delta = xd[r] + xd[128 + r];
       mbar_wait(s_full, (uint32_t)i & 1);
       tcgen05_fence_after();
-      // pass 1: P and P~ dP for this thread's (at most four) 16-key blocks; P~ goes to smem right away.
-      // Branch-free per element; rows past Nq see zero-filled Q / dO rows (finite P, dP = 0) and are never stored.
-      float pk[4][16], ck[4][16];
-      float delta = 0.f;
-#pragma unroll
+      // one pass: P = exp2(S - lse), P~ = dropout(P), dS = P~ dP - P delta.  Branch-free per element; rows past Nq see
+      // zero-filled Q / dO rows (finite P, dP = 0, delta = 0) and are never stored.
+#pragma unroll 1
       for (int t = 0; t < 4; ++t) {
         const int kb = ch + 2 * t;
         if (live_q && kb < nblk) {
           uint32_t rs[16], rp[16];
-          float kv[16], pt[16];
+          float kv[16], pt[16], ds[16];
           tmem_ld_32x32b_x16(t_lane + COL_S + kb * 16, rs);
           tmem_ld_32x32b_x16(t_lane + COL_DP + kb * 16, rp);
           load_kv16(km, brow, kb * 16, p.Nk, kv);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            pk[t][j] = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, kv[j]) - lse);
-            pt[j] = pk[t][j];
+            const float pr = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, kv[j]) - lse);
+            pt[j] = pr;
+            ds[j] = -pr * delta;
           }
           if (drop) drop_mul16(pt, attn_drop_rowkey(seed, b, p.heads, h, p.Nq, r), kb * 16, thr16, keep_scale);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            ck[t][j] = pt[j] * __uint_as_float(rp[j]);
-            delta += ck[t][j];
-          }
-          store_row16<T>(sP, r, kb * 16, pt);
-        }
-      }
-      xd[ch * 128 + r] = delta;
-      compute_bar();
-      delta += xd[(ch ^ 1) * 128 + r];
-      // pass 2: dS = P~ dP - P delta
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int kb = ch + 2 * t;
-        if (live_q && kb < nblk) {
-          float ds[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) ds[j] = fmaf(-pk[t][j], delta, ck[t][j]);
+          for (int j = 0; j < 16; ++j) ds[j] = fmaf(pt[j], __uint_as_float(rp[j]), ds[j]);
           if (dbrow && rv) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (kb * 16 + j < p.Nk) atomicAdd(dbrow + kb * 16 + j, ds[j]);
           }
+          store_row16<T>(sP, r, kb * 16, pt);
           store_row16<T>(sdS, r, kb * 16, ds);
         }
       }
@@ -557,11 +570,18 @@ void fill(const goat_attn_args* a, PArgs* t) {
   t->dbias = a->dbias;
 }
 
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 template <typename T>
 int fwd_launch(const goat_attn_args* a, cudaStream_t st) {
   static bool cfg = false;
+  static const int two = env_flag("GOAT_ATTN_FWD_2CTA", 1);
   if (!cfg) {
-    GOAT_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    GOAT_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<T, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem<3>()));
+    GOAT_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<T, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem<1>()));
     cfg = true;
   }
   CUtensorMap tq, tk, tv;
@@ -572,8 +592,14 @@ int fwd_launch(const goat_attn_args* a, cudaStream_t st) {
   if ((rc = make_tmap3(&tv, a->dtype, a->V, cols, a->Nk, a->B, a->ldv, a->sbv, 64, 128))) return rc;
   PArgs t;
   fill(a, &t);
-  const int grid = t.n_items < num_sms() ? t.n_items : num_sms();
-  GOAT_CUDA(launch_pdl(attn_fwd_pipe_kernel<T>, dim3(grid), dim3(P_THREADS), (size_t)F_SMEM, st, tq, tk, tv, t));
+  if (two && t.n_items > num_sms()) {
+    const int slots = 2 * num_sms();
+    const int grid = t.n_items < slots ? t.n_items : slots;
+    GOAT_CUDA(launch_pdl(attn_fwd_pipe_kernel<T, 1, 2>, dim3(grid), dim3(P_THREADS), (size_t)f_smem<1>(), st, tq, tk, tv, t));
+  } else {
+    const int grid = t.n_items < num_sms() ? t.n_items : num_sms();
+    GOAT_CUDA(launch_pdl(attn_fwd_pipe_kernel<T, 3, 1>, dim3(grid), dim3(P_THREADS), (size_t)f_smem<3>(), st, tq, tk, tv, t));
+  }
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }
