@@ -95,6 +95,10 @@ typedef struct goat_gemm_args {
   int accumulate; /* 1: out (fp32) += alpha * A B^T, reduced with fp32 atomics; the tcgen05 kernel then also splits K
                      across CTAs when M x N alone cannot fill the GPU (weight gradients: K = tokens).  No bias / res /
                      act / dropout / out2 in this mode; the caller zero-initialises out. */
+  const void* B_lo; /* optional second weight operand with B's layout: acc = A B^T + A B_lo^T in one launch (the K loop runs
+                       twice over A).  B = fp16(W), B_lo = fp16(W - B): the weight then carries ~22 mantissa bits, which
+                       removes the systematic weight-rounding error of the 16-bit forward pass (profiles/
+                       r02_fp16_error_budget.txt).  tcgen05 path only, B K-major, no split-K. */
 } goat_gemm_args;
 int goat_gemm(const goat_gemm_args* args, goat_stream_t stream);
 
@@ -109,9 +113,9 @@ int goat_gemm(const goat_gemm_args* args, goat_stream_t stream);
  * P/model/ops.py:25-34, or -inf for the pano encoder's key_padding_mask); bias is the additive
  * [B,Nq,Nk] term (graph_sprels, :690-691).  lse[b,h,q] (log-sum-exp of the scaled scores) is
  * saved for backward.  drop_p/seed: attention-probability dropout (:280).
- * D must be 64.  F16/BF16 with Nq <= 128, 16-byte aligned bases and ld/sb multiples of 8 run on tcgen05
- * (TMA-staged Q/K/V tiles, S and O accumulators in TMEM, keys in chunks of 128); everything else, and F32,
- * runs the fp32-math SIMT kernels.
+ * D must be 64.  F16/BF16 with 16-byte aligned bases and ld/sb multiples of 8 run on tcgen05 (TMA-staged Q/K/V tiles, S
+ * and O accumulators in TMEM): the persistent pipelined kernels for Nq, Nk <= 128, 128-row query tiles x 128-key chunks
+ * beyond (long instructions); everything else, and F32, runs the fp32-math SIMT kernels.
  * ------------------------------------------------------------------------------------------ */
 typedef struct goat_attn_args {
   int B, heads, Nq, Nk, D;
@@ -205,12 +209,14 @@ int goat_dropout_cast(const void* src, int src_dtype, void* dst, int dst_dtype, 
  *               351-363).  Gradients are additionally divided by scaler[0]; a non-finite norm SKIPS the update (only
  *               g is cleared); bias corrections come from scaler[4] + 1.  goat_scaler_update (one thread) then
  *               applies GradScaler.update(): scale *= backoff after an overflow, *= growth after `interval` clean steps.
+ *   shadow_lo (optional, same dtype as shadow): shadow_lo = round(p - shadow), the second term of the split weight
+ *               operand (goat_gemm_args.B_lo).
  * ------------------------------------------------------------------------------------------ */
 size_t goat_sumsq_workspace_bytes(void);
 int goat_sumsq(const float* g, long long n, float* partial, int* nparts_out, goat_stream_t stream);
 int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
                     long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
-                    int zero_grad, const float* scaler, goat_stream_t stream);
+                    int zero_grad, const float* scaler, void* shadow_lo, goat_stream_t stream);
 int goat_scaler_update(float* scaler, const float* partial, int nparts, float growth, float backoff, int interval,
                        goat_stream_t stream);
 

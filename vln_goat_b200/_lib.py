@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("drop_seed", C.c_uint64), ("drop_seed_ptr", C.c_void_p),
         ("force_simt", C.c_int),
         ("accumulate", C.c_int),
+        ("B_lo", C.c_void_p),
     ]
 
 
@@ -77,7 +78,7 @@ SYMBOLS = {
     "goat_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "goat_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong,
                                   C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                  C.c_void_p]),
+                                  C.c_void_p, C.c_void_p]),
     "goat_scaler_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "goat_act_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "goat_act_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),

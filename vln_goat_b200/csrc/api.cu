@@ -85,6 +85,8 @@ int goat_gemm(const goat_gemm_args* a, goat_stream_t stream_) {
   ep.drop_seed = a->drop_seed;
   ep.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(a->drop_seed_ptr);
   ep.drop_row0 = 0;
+  GOAT_CHECK(!a->B_lo || (a->dtype != GOAT_F32 && !a->b_mn_major && !a->accumulate && aligned16(a->B_lo)),
+             "goat_gemm: B_lo needs 16-bit operands, a K-major B, no accumulate mode and a 16-byte aligned pointer");
   if (!a->force_simt && gemm_umma_eligible(*a)) {
     GOAT_CHECK(aligned16(a->out) && (!a->out2 || aligned16(a->out2)) && (!a->res || aligned16(a->res)) &&
                    (!a->aux_in || aligned16(a->aux_in)) && (!a->aux_out || aligned16(a->aux_out)) &&
@@ -92,6 +94,7 @@ int goat_gemm(const goat_gemm_args* a, goat_stream_t stream_) {
                "goat_gemm: tensor base pointers must be 16-byte aligned");
     return gemm_umma(*a, ep, stream);
   }
+  GOAT_CHECK(!a->B_lo, "goat_gemm: B_lo is a tcgen05-path operand (K >= 16, leading dimensions multiples of 8)");
   return gemm_simt(*a, ep, stream);
 }
 

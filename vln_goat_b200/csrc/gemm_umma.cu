@@ -44,6 +44,7 @@ struct Cfg {
 
 struct Sched {
   int tiles_m, tiles_n, splits, kb_per_split, num_kb, num_tiles;
+  int kb_wrap;   // > 0: k-blocks [kb_wrap, num_kb) re-read A from k-block (kb - kb_wrap) against the second B operand (B_lo)
 };
 
 __device__ __forceinline__ void tile_coords(const Sched& sc, int t, int& m0, int& n0, int& kb0, int& kb1) {
@@ -133,7 +134,8 @@ __device__ __forceinline__ void epi_store1(const EpiParams& ep, int m, int n, fl
 
 template <typename T, int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep,
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmB2, EpiParams ep,
                  int M, int N, int K, Sched sc) {
   static_assert(BLOCK_N == 128, "tile scheduler and TMEM double buffering assume 128-wide tiles");
   using C = Cfg<BLOCK_N, STAGES>;
@@ -185,7 +187,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          const int k0 = kb * BLOCK_K;
+          const bool lo = sc.kb_wrap > 0 && kb >= sc.kb_wrap;
+          const int k0 = (lo ? kb - sc.kb_wrap : kb) * BLOCK_K;
+          const CUtensorMap* mapB = lo ? &tmB2 : &tmB;
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 m}
           } else {
@@ -194,11 +198,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, k0);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BLOCK_N n}
+            tma_load_2d(sb, mapB, &full_bar[s], k0, n0);  // box {64 k, BLOCK_N n}
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+              tma_load_2d(sb + j * 8192, mapB, &full_bar[s], n0 + 64 * j, k0);
           }
         }
       }
@@ -388,6 +392,9 @@ int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   if (!B_MN) rc = make_tmap(&tmB, a.dtype, a.B, a.K, a.N, a.ldb, BLOCK_K, BLOCK_N);
   else rc = make_tmap(&tmB, a.dtype, a.B, a.N, a.K, a.ldb, 64, BLOCK_K);
   if (rc) return rc;
+  CUtensorMap tmB2 = tmB;
+  const bool use_lo = a.B_lo != nullptr && !B_MN && !ep.accumulate;
+  if (use_lo && (rc = make_tmap(&tmB2, a.dtype, a.B_lo, a.K, a.N, a.ldb, BLOCK_K, BLOCK_N))) return rc;
   Sched sc;
   sc.tiles_m = (a.M + BLOCK_M - 1) / BLOCK_M;
   sc.tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
@@ -401,11 +408,16 @@ int launch(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
     if (cap < 1) cap = 1;
     sc.splits = want < cap ? want : cap;
   }
+  sc.kb_wrap = 0;
+  if (use_lo) {            // second pass of the K loop over A against B_lo (never combined with split-K)
+    sc.kb_wrap = sc.num_kb;
+    sc.num_kb *= 2;
+  }
   sc.kb_per_split = (sc.num_kb + sc.splits - 1) / sc.splits;
   sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
   sc.num_tiles = mn * sc.splits;
   const int grid = sc.num_tiles < num_sms() ? sc.num_tiles : num_sms();
-  GOAT_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, ep, a.M, a.N, a.K, sc));
+  GOAT_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmB2, ep, a.M, a.N, a.K, sc));
   return GOAT_OK;
 }
 

@@ -60,6 +60,7 @@ struct Cfg2 {
 
 struct Sched2 {
   int tiles_m, tiles_n, splits, kb_per_split, num_kb, num_tiles;
+  int kb_wrap;   // > 0: k-blocks [kb_wrap, num_kb) re-read A from k-block (kb - kb_wrap) against the second B operand (B_lo)
 };
 
 template <int BN>
@@ -333,8 +334,8 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
 
 template <typename T, int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep,
-                  int M, int N, int K, Sched2 sc, int epi_mode) {
+gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmB2, EpiParams ep, int M, int N, int K, Sched2 sc, int epi_mode) {
   static_assert(BN == 128 || BN == 256, "pair tile is 256 x 128 or 256 x 256");
   using C = Cfg2<BN, STAGES>;
   constexpr int BNH = BN / 2;       // B rows staged by each CTA
@@ -357,6 +358,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (sc.kb_wrap > 0) tma_prefetch_desc(&tmB2);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);    // the leader's producer (arrive.expect_tx of both CTAs' bytes)
@@ -394,7 +396,9 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          const int k0 = kb * BK;
+          const bool lo = sc.kb_wrap > 0 && kb >= sc.kb_wrap;
+          const int k0 = (lo ? kb - sc.kb_wrap : kb) * BK;
+          const CUtensorMap* mapB = lo ? &tmB2 : &tmB;
           if (!A_MN) {
             tma_load_2d_2sm(sa, &tmA, fb, k0, my_m);  // box {64 k, 128 m}
           } else {
@@ -403,11 +407,11 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_2d_2sm(sa + j * 8192, &tmA, fb, my_m + 64 * j, k0);
           }
           if (!B_MN) {
-            tma_load_2d_2sm(sb, &tmB, fb, k0, my_n);  // box {64 k, BNH n}
+            tma_load_2d_2sm(sb, mapB, fb, k0, my_n);  // box {64 k, BNH n}
           } else {
 #pragma unroll
             for (int j = 0; j < BNH / 64; ++j)
-              tma_load_2d_2sm(sb + j * 8192, &tmB, fb, my_n + 64 * j, k0);
+              tma_load_2d_2sm(sb + j * 8192, mapB, fb, my_n + 64 * j, k0);
           }
         }
       }
@@ -510,6 +514,9 @@ int launch2(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   if (!B_MN) rc = make_tmap(&tmB, a.dtype, a.B, a.K, a.N, a.ldb, BK, BN / 2);
   else rc = make_tmap(&tmB, a.dtype, a.B, a.N, a.K, a.ldb, 64, BK);
   if (rc) return rc;
+  CUtensorMap tmB2 = tmB;
+  const bool use_lo = a.B_lo != nullptr && !B_MN && !ep.accumulate;
+  if (use_lo && (rc = make_tmap(&tmB2, a.dtype, a.B_lo, a.K, a.N, a.ldb, BK, BN / 2))) return rc;
   const int pairs = num_sms() / 2;
   Sched2 sc;
   sc.tiles_m = (a.M + 2 * BM - 1) / (2 * BM);
@@ -533,11 +540,16 @@ int launch2(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
     }
     sc.splits = best;
   }
+  sc.kb_wrap = 0;
+  if (use_lo) {            // second pass of the K loop over A against B_lo (never combined with split-K)
+    sc.kb_wrap = sc.num_kb;
+    sc.num_kb *= 2;
+  }
   sc.kb_per_split = (sc.num_kb + sc.splits - 1) / sc.splits;
   sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
   sc.num_tiles = mn * sc.splits;
   const int clusters = sc.num_tiles < pairs ? sc.num_tiles : pairs;
-  GOAT_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, ep, a.M, a.N, a.K, sc,
+  GOAT_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmB2, ep, a.M, a.N, a.K, sc,
                        epi_mode_of(ep)));
   return GOAT_OK;
 }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              TS* __restrict__ shadow, long long n, long long n_decay, const float* __restrict__ hp,
              const float* __restrict__ partial, int nparts, float* __restrict__ norm_out, int zero_grad,
-             const float* __restrict__ scaler) {
+             const float* __restrict__ scaler, TS* __restrict__ shadow_lo) {
   __shared__ float s_coef;
   __shared__ int s_skip;
   if (threadIdx.x < 32) {
@@ -116,6 +116,13 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
         w.x = pack2<TS>(pp.x, pp.y);
         w.y = pack2<TS>(pp.z, pp.w);
         reinterpret_cast<uint2*>(shadow)[i] = w;
+        if (shadow_lo) {   // second term of the split weight: what the 16-bit copy lost
+          const float2 h0 = unpack2<TS>(w.x), h1 = unpack2<TS>(w.y);
+          uint2 l;
+          l.x = pack2<TS>(pp.x - h0.x, pp.y - h0.y);
+          l.y = pack2<TS>(pp.z - h1.x, pp.w - h1.y);
+          reinterpret_cast<uint2*>(shadow_lo)[i] = l;
+        }
       }
     }
   }
@@ -128,7 +135,12 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
       if (i < n_decay) x -= x * (lr * wd);
       p[i] = x; m[i] = mi; v[i] = vi;
       if (zero_grad) g[i] = 0.f;
-      if (shadow) { if constexpr (sizeof(TS) == 2) shadow[i] = from_f<TS>(x); }
+      if (shadow) {
+        if constexpr (sizeof(TS) == 2) {
+          shadow[i] = from_f<TS>(x);
+          if (shadow_lo) shadow_lo[i] = from_f<TS>(x - to_f<TS>(shadow[i]));
+        }
+      }
     }
   }
 }
@@ -174,22 +186,23 @@ extern "C" int goat_sumsq(const float* g, long long n, float* partial, int* npar
 
 extern "C" int goat_adamw_step(float* p, float* g, float* m, float* v, void* shadow, int shadow_dtype, long long n,
                                long long n_decay, const float* hp, const float* partial, int nparts, float* norm_out,
-                               int zero_grad, const float* scaler, goat_stream_t stream) {
+                               int zero_grad, const float* scaler, void* shadow_lo, goat_stream_t stream) {
   GOAT_CHECK(p && g && m && v && hp && partial, "goat_adamw_step: null argument");
   GOAT_CHECK(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || aligned16(shadow)),
              "goat_adamw_step: buffers must be 16-byte aligned");
   GOAT_CHECK(!shadow || shadow_dtype == GOAT_F16 || shadow_dtype == GOAT_BF16, "goat_adamw_step: shadow dtype must be F16/BF16");
+  GOAT_CHECK(!shadow_lo || (shadow && aligned16(shadow_lo)), "goat_adamw_step: shadow_lo needs shadow and 16-byte alignment");
   GOAT_CHECK(nparts >= 1 && nparts <= SUMSQ_MAX_PARTS, "goat_adamw_step: bad nparts");
   if (n <= 0) return GOAT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long want = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   const int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
   if (shadow && shadow_dtype == GOAT_F16)
-    adamw_kernel<__half><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__half*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler);
+    adamw_kernel<__half><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__half*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler, (__half*)shadow_lo);
   else if (shadow)
-    adamw_kernel<__nv_bfloat16><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler);
+    adamw_kernel<__nv_bfloat16><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler, (__nv_bfloat16*)shadow_lo);
   else
-    adamw_kernel<float><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (float*)nullptr, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler);
+    adamw_kernel<float><<<grid, OPT_THREADS, 0, st>>>(p, g, m, v, (float*)nullptr, n, n_decay, hp, partial, nparts, norm_out, zero_grad, scaler, (float*)nullptr);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

@@ -105,7 +105,17 @@ class FlatParams(object):
         self.m = torch.zeros(tot, device=dev, dtype=torch.float32)
         self.v = torch.zeros(tot, device=dev, dtype=torch.float32)
         self.shadow_dtype = shadow_dtype if shadow_dtype in (torch.float16, torch.bfloat16) else None
-        self.shadow = torch.zeros(tot, device=dev, dtype=self.shadow_dtype) if self.shadow_dtype else None
+        from . import runtime
+        self.split = bool(self.shadow_dtype) and runtime.weight_split()
+        self.shadow = self.shadow_lo = None
+        if self.shadow_dtype:
+            # [hi | lo] when weights are split (runtime.set_weight_split): lo = round(p - hi), written by the optimizer kernel
+            buf = torch.zeros(tot * (2 if self.split else 1), device=dev, dtype=self.shadow_dtype)
+            self.shadow = buf[:tot]
+            if self.split:
+                self.shadow_lo = buf[tot:]
+                runtime.register_split_buffer(buf, tot)
+            self._shadow_buf = buf
         self._g_shard = self._x_shard = None
         self.master_synced = True
         self.scaler = None
@@ -159,6 +169,8 @@ class FlatParams(object):
         from . import runtime
         if self.shadow is not None:
             ops.cast(self.p, self.shadow_dtype, out=self.shadow)
+            if self.shadow_lo is not None:
+                self.shadow_lo.copy_(self.p - self.shadow.float())
         runtime.bump_generation()
 
     def begin_step(self):
@@ -234,12 +246,17 @@ class FlatParams(object):
                                      self.v[lo:lo + S].data_ptr(),
                                      self.shadow[lo:lo + S].data_ptr() if self.shadow is not None else None, sd, S,
                                      n_decay_local, self._hp.data_ptr(), self._partial.data_ptr(), 1,
-                                     self.grad_norm.data_ptr(), 0, _p_or_none(self.scaler), st), "goat_adamw_step")
+                                     self.grad_norm.data_ptr(), 0, _p_or_none(self.scaler),
+                                     self.shadow_lo[lo:lo + S].data_ptr() if self.shadow_lo is not None else None, st),
+                   "goat_adamw_step")
         ops.LAUNCHES[0] += 2
         self._scaler_update(1, st)
         if self.shadow is not None:
             self._x_shard.copy_(self.shadow[lo:lo + S])
             D.all_gather_flat(self.shadow, self._x_shard, self.group)
+            if self.shadow_lo is not None:
+                self._x_shard.copy_(self.shadow_lo[lo:lo + S])
+                D.all_gather_flat(self.shadow_lo, self._x_shard, self.group)
             # everything the kernels read in FP32 (embedding tables, LayerNorm gains, pooling / gate vectors, biases):
             # each owner broadcasts its piece of [n_shadow_only, numel)
             for r, a, b in D.tail_pieces(self.n_shadow_only, self.numel, S, W):
@@ -274,7 +291,8 @@ class FlatParams(object):
         _lib.check(L.goat_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                      self.shadow.data_ptr() if self.shadow is not None else None, sd, self.numel,
                                      self.n_decay, self._hp.data_ptr(), self._partial.data_ptr(), nparts.value,
-                                     self.grad_norm.data_ptr(), 1, _p_or_none(self.scaler), st), "goat_adamw_step")
+                                     self.grad_norm.data_ptr(), 1, _p_or_none(self.scaler), _p_or_none(self.shadow_lo), st),
+                   "goat_adamw_step")
         ops.LAUNCHES[0] += 2
         self._scaler_update(nparts.value, st)
         from . import runtime

@@ -112,12 +112,19 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, res=None, aux_in=None, aux_
     a.drop_seed_ptr = None if seed_ptr is None else seed_ptr.data_ptr()
     a.force_simt = int(force_simt)
     a.accumulate = int(accumulate)
+    umma_ok = a.dtype != F32 and K >= 16 and lda % 8 == 0 and ldb % 8 == 0 and not force_simt
+    if umma_ok and not b_mn and not accumulate:
+        # forward GEMM against a split weight ([hi | lo] buffer registered in runtime): add the lo term in the same launch
+        from . import runtime
+        lo = runtime.lo_pointer(B)
+        if lo is not None:
+            a.B_lo = lo
     _lib.check(_lib.lib().goat_gemm(C.byref(a), _stream()), "goat_gemm")
     LAUNCHES[0] += 1
     if GEMM_LOG is not None:
-        umma = a.dtype != F32 and K >= 16 and lda % 8 == 0 and ldb % 8 == 0 and not force_simt
-        GEMM_LOG.append((M, N, K, int(a_mn), int(b_mn), a.dtype, int(not umma), int(accumulate), int(act), int(bias is not None),
-                         int(res is not None), int(out.dtype == torch.float32), int(drop_p > 0.0), int(out2 is not None)))
+        GEMM_LOG.append((M, N, K, int(a_mn), int(b_mn), a.dtype, int(not umma_ok), int(accumulate), int(act), int(bias is not None),
+                         int(res is not None), int(out.dtype == torch.float32), int(drop_p > 0.0), int(out2 is not None),
+                         int(bool(a.B_lo))))
     return out
 
 

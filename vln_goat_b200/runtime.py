@@ -54,6 +54,65 @@ def compute(dtype):
         set_compute_dtype(prev)
 
 
+# ---------------------------------------------------------------------------------------------
+# Split weights.  A 16-bit copy of a weight carries 11 (fp16) / 8 (bf16) mantissa bits, and that rounding error is
+# SYSTEMATIC: the same for every token, so attention / pooling do not average it out -- it alone costs the CFP embeddings
+# ~9e-4 of the 1e-3 budget (profiles/r02_fp16_error_budget.txt).  With split weights every 16-bit weight buffer is
+# allocated as [hi | lo] (lo = round(W - hi)); goat_gemm runs the K loop twice over the activations (hi, then lo) for
+# FORWARD GEMMs (K-major weight operand), so the weight enters with ~22 bits.  Backward GEMMs read hi only.
+# ops.gemm finds the lo half of any view into a registered buffer by pointer arithmetic: no plumbing through the
+# autograd functions.
+# ---------------------------------------------------------------------------------------------
+_weight_split = True
+_split_buffers = {}     # base data_ptr of a [hi | lo] buffer -> (bytes of the hi half, the tensor kept alive)
+
+
+def weight_split():
+    return _weight_split
+
+
+def set_weight_split(on):
+    """Forward GEMMs use hi + lo 16-bit weight operands (default) or the plain 16-bit copy (~8 % faster step, forward
+    error ~1.6x larger).  Set before FlatParams / the first forward."""
+    global _weight_split
+    _weight_split = bool(on)
+    bump_generation()
+
+
+def register_split_buffer(buf, hi_numel):
+    """buf: 1-D 16-bit tensor of 2 * hi_numel elements, [hi | lo]"""
+    _split_buffers[buf.data_ptr()] = (hi_numel * buf.element_size(), buf)
+    if len(_split_buffers) > 4096:                 # per-parameter cast caches of long-dead models
+        for k in list(_split_buffers)[:2048]:
+            del _split_buffers[k]
+
+
+def lo_pointer(t):
+    """device address of the lo twin of a view into a registered [hi | lo] buffer (None if t is not such a view)"""
+    if not _weight_split or not _split_buffers:
+        return None
+    base = t.untyped_storage().data_ptr()
+    ent = _split_buffers.get(base)
+    if ent is None:
+        return None
+    off = t.data_ptr() - base
+    if off < 0 or off + (t.numel() and 1) > ent[0]:
+        return None
+    return t.data_ptr() + ent[0]
+
+
+def _cast_split(p32, cdt):
+    """[hi | lo] 16-bit copy of a contiguous fp32 tensor -> the hi view (shape of p32); lo is found via lo_pointer"""
+    n = p32.numel()
+    npad = (n + 7) // 8 * 8
+    buf = torch.empty(2 * npad, device=p32.device, dtype=cdt)
+    hi = buf[:n].view(p32.shape)
+    ops.cast(p32, cdt, out=buf[:n])
+    buf[npad:npad + n].copy_((p32.reshape(-1) - buf[:n].float()))
+    register_split_buffer(buf, npad)
+    return hi
+
+
 def _adjacent(ts):
     """True when the tensors are contiguous and laid out back to back in one storage."""
     for a, b in zip(ts[:-1], ts[1:]):
@@ -88,7 +147,7 @@ def wc(param, cdt=None):
     ent = getattr(param, "_goat_cast", None)
     if ent is not None and ent[0] == key and ent[1].dtype == cdt and ent[1].device == p.device:
         return ent[1]
-    t = ops.cast(p.contiguous(), cdt)
+    t = _cast_split(p.contiguous(), cdt) if _weight_split else ops.cast(p.contiguous(), cdt)
     param._goat_cast = (key, t)
     return t
 
@@ -110,6 +169,6 @@ def wc_cat(params, cdt=None):
     if ent is not None and ent[0] == key and ent[2] == tuple(id(p) for p in params) and ent[1].device == params[0].device:
         return ent[1]
     cat = torch.cat([p.detach() for p in params], dim=0)
-    t = cat if cdt == torch.float32 else ops.cast(cat, cdt)
+    t = cat if cdt == torch.float32 else (_cast_split(cat, cdt) if (_weight_split and cat.dim() == 2) else ops.cast(cat, cdt))
     params[0]._goat_cat = (key, t, tuple(id(p) for p in params))
     return t
