@@ -231,38 +231,50 @@ class Clocks(object):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class Prefetcher(object):
-    """Background host worker: batch dict -> prepare_pretrain -> pinned staging buffers, one step ahead (the reference
-    overlaps collate with compute the same way: DataLoader workers + PrefetchLoader, P/data/loader.py:62-130)."""
+    """Background host workers: batch dict -> prepare_pretrain (index builders, padding straight into pinned memory) a
+    few steps ahead, results handed out in step order (the reference overlaps collate with compute the same way:
+    DataLoader workers + PrefetchLoader, P/data/loader.py:62-130)."""
 
-    def __init__(self, batches, pad, depth=2):
-        import queue
-        self.batches, self.pad = batches, pad
-        self.q = queue.Queue(maxsize=depth)
-        self.n = 0
+    def __init__(self, batches, pad, depth=4, workers=2):
+        self.batches, self.pad, self.depth, self.workers = batches, pad, depth, workers
+        self.cv = threading.Condition()
+        self.ready = {}
+        self.next_get = 0
         self.stop = False
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        self.threads = [threading.Thread(target=self._run, args=(w,), daemon=True) for w in range(workers)]
+        for t in self.threads:
+            t.start()
 
-    def _run(self):
+    def _run(self, w):
         from vln_goat_b200 import batching
-        i = 0
+        i = w
         while not self.stop:
+            with self.cv:
+                while not self.stop and i >= self.next_get + self.depth:
+                    self.cv.wait(0.05)
+            if self.stop:
+                return
             task = TASKS[i % 3]
             b = self.batches[(i // 3) % len(self.batches)]
-            P = batching.pin(batching.prepare_pretrain(b, task, pad=self.pad))
-            while not self.stop:
-                try:
-                    self.q.put((task, P), timeout=0.1)
-                    break
-                except Exception:
-                    continue
-            i += 1
+            P = batching.pin(batching.prepare_pretrain(b, task, pad=self.pad, pinned=True))
+            with self.cv:
+                self.ready[i] = (task, P)
+                self.cv.notify_all()
+            i += self.workers
 
     def get(self):
-        return self.q.get()
+        with self.cv:
+            while self.next_get not in self.ready:
+                self.cv.wait(0.05)
+            item = self.ready.pop(self.next_get)
+            self.next_get += 1
+            self.cv.notify_all()
+        return item
 
     def close(self):
         self.stop = True
+        with self.cv:
+            self.cv.notify_all()
 
 
 def run_goat(args):

@@ -36,19 +36,27 @@ def _cpu(t):
     return t.detach().cpu() if torch.is_tensor(t) and t.is_cuda else t
 
 
-def _pad_dim0(t, n, value=0):
-    if t.shape[0] == n:
+def _pad_dim0(t, n, value=0, pinned=False):
+    """pad the leading dimension to n; pinned=True: the result lives in page-locked host memory (ONE copy does the
+    padding and the staging for the H2D transfer)"""
+    pinned = pinned and not t.is_cuda
+    if t.shape[0] == n and not pinned:
         return t
-    out = t.new_full((n,) + tuple(t.shape[1:]), value)
+    out = torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device, pin_memory=pinned)
     out[:t.shape[0]] = t
+    if n > t.shape[0]:
+        out[t.shape[0]:] = value
     return out
 
 
-def _pad_dim1(t, n, value=0):
-    if t.shape[1] == n:
+def _pad_dim1(t, n, value=0, pinned=False):
+    pinned = pinned and not t.is_cuda
+    if t.shape[1] == n and not pinned:
         return t
-    out = t.new_full((t.shape[0], n) + tuple(t.shape[2:]), value)
+    out = torch.empty((t.shape[0], n) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device, pin_memory=pinned)
     out[:, :t.shape[1]] = t
+    if n > t.shape[1]:
+        out[:, t.shape[1]:] = value
     return out
 
 
@@ -56,10 +64,11 @@ _Z_KEYS = ("instr_z_direction_features", "instr_z_direction_pzs", "instr_z_landm
            "img_z_features", "img_z_pzs")
 
 
-def prepare_pretrain(batch, task, pad=None, pano_fusion=True):
+def prepare_pretrain(batch, task, pad=None, pano_fusion=True, pinned=False):
     """batch: dict with the keys of P/data/tasks.py's collates, tensors on the host or on the
     device.  -> dict of tensors (same placement as the inputs; integer index tensors are built on the host).
-    pano_fusion: config.adaptive_pano_fusion (a visited node is its fused panorama, else the mean of its views)."""
+    pano_fusion: config.adaptive_pano_fusion (a visited node is its fused panorama, else the mean of its views).
+    pinned: write the large host tensors (view / location features) straight into page-locked memory."""
     task = task.split("_")[0]
     if task not in ("mlm", "sap", "cfp"):
         raise NotImplementedError("task %r is outside the hot-path scope (MRC / OG are REVERIE-only)" % task)
@@ -107,7 +116,7 @@ def prepare_pretrain(batch, task, pad=None, pano_fusion=True):
         raise ValueError("the batch has %d tokens per instruction, more than the padded length %d" % (L, Lp))
     out = {
         "txt_ids": _pad_dim1(txt_ids, Lp), "txt_lens": batch["txt_lens"],
-        "view_fts": _pad_dim0(feats, Sp), "loc_fts": _pad_dim0(batch["traj_loc_fts"], Sp),
+        "view_fts": _pad_dim0(feats, Sp, 0, pinned), "loc_fts": _pad_dim0(batch["traj_loc_fts"], Sp, 0, pinned),
         "view_lens": _pad_dim0(view_lens, Sp, 1), "last_rows": put(last_rows),
         "gmap_idx_f": put(idx_f.contiguous()), "gmap_idx_v": put(idx_v.contiguous()),
         "gmap_step_ids": _pad_dim1(gmap_step_ids, Gp), "gmap_pos_fts": _pad_dim1(batch["gmap_pos_fts"], Gp),
@@ -153,8 +162,8 @@ def prepare_pretrain(batch, task, pad=None, pano_fusion=True):
 
 
 def pin(prepared):
-    """Copies of the (host) tensors in pinned memory, ready for non-blocking H2D copies."""
-    return {k: (v.pin_memory() if not v.is_cuda else v) for k, v in prepared.items()}
+    """The (host) tensors in pinned memory, ready for non-blocking H2D copies (already-pinned ones are kept)."""
+    return {k: (v if (v.is_cuda or v.is_pinned()) else v.pin_memory()) for k, v in prepared.items()}
 
 
 def h2d_bytes(prepared):

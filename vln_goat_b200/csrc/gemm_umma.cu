@@ -342,6 +342,23 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint
   return GOAT_OK;
 }
 
+// same 2-D map with the 64-byte swizzle: 32-column x 16-bit output tiles of the TMA-store epilogue (gemm_umma2.cu)
+int make_tmap_sw64(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                   uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_tiled();
+  GOAT_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstr[1] = {ld_elems * 2};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == GOAT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GOAT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store) failed with CUresult %d (inner %llu outer %llu ld %llu)", (int)r,
+             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems);
+  return GOAT_OK;
+}
+
 // 3-D map over a token-major [d2 = batch][d1 = token][d0 = channel] tensor (channel contiguous, token stride ld,
 // batch stride sb, in elements); boxes of box0 channels x box1 tokens x 1 batch, 128B swizzle, zero OOB fill.
 int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,

@@ -20,6 +20,7 @@
 //               TMEM reads and math.  Both CTAs' epilogue warps release the accumulator on the leader's barrier.
 // Split-K (accumulate mode), K-major / MN-major operands and ragged edges as in gemm_umma.cu.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,6 +28,8 @@ namespace goat {
 
 int make_tmap(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
               uint32_t box_inner, uint32_t box_outer);
+int make_tmap_sw64(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                   uint32_t box_inner, uint32_t box_outer);
 int num_sms();
 
 #ifdef GOAT_TIMELINE
@@ -44,7 +47,9 @@ constexpr int UK = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int PATCH_LD = 36;                 // floats per staged row (32 + 4 padding: conflict-free both ways)
-constexpr int PATCH_FLOATS = 32 * PATCH_LD;  // one warp's 32 x 32 transpose patch
+constexpr int PATCH_FLOATS = 1280;           // one warp's staging area: the 32 x 36 fp32 transpose patch (4608 B) or two
+                                             // 2 KB TMA-store tiles (32 rows x 32 x 16 bit, 64B swizzle); 5120 B keeps every
+                                             // warp's area 512-byte aligned, which the swizzle pattern needs
 
 template <int BN, int STAGES>
 struct Cfg2 {
@@ -137,8 +142,27 @@ enum {
   EPI_GELU = 2,    // [bias] -> 16-bit pre-activation (aux_out) -> GELU, [dropout] -> 16-bit out
   EPI_DGELU = 3,   // * gelu'(aux_in), [dropout] -> 16-bit out
   EPI_RES32 = 4,   // [bias], [dropout], [+ res] -> fp32 out (+ optional 16-bit copy out2)
-  EPI_GENERIC = 5  // anything else (ReLU / tanh heads, unaligned leading dimensions): predicated scalar path
+  EPI_GENERIC = 5, // anything else (ReLU / tanh heads, unaligned leading dimensions): predicated scalar path
+  // 16-bit outputs through TMA stores: TMEM -> registers (one accumulator row per lane) -> 2 KB swizzled smem tile ->
+  // cp.async.bulk.tensor store.  No fp32 transpose through shared memory (which competed with the MMA's operand reads and
+  // slowed the main loop of the next tile by 25-70 %, profiles/r02g_timeline.log), no per-lane global addressing, ragged
+  // edges clipped by the hardware.
+  EPI_T16_TMA = 6, EPI_GELU_TMA = 7, EPI_DGELU_TMA = 8
 };
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16-byte chunk q (8 x 16-bit) of row `row` in a [32 rows][64 B] tile with the 64-byte swizzle (address bits 4-5 ^= bits 7-8)
+__device__ __forceinline__ uint8_t* sw64_chunk(uint8_t* tile, int row, int q) {
+  return tile + row * 64 + ((q ^ ((row >> 1) & 3)) << 4);
+}
 
 // operands of one 32 x 32 patch that do not depend on the accumulator: row (i*4 + lane/8), columns (lane%8)*4..+3
 template <int MODE>
@@ -332,10 +356,130 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& ep, const Sched2&
   }
 }
 
+// MODE: EPI_T16 (alpha, bias), EPI_GELU (bias -> z tile -> GELU [dropout] -> out tile), EPI_DGELU (* gelu'(aux_in) [dropout])
+template <typename T, int BN, int MODE>
+__device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Sched2& sc, const EpiCtx& cx,
+                                                  const CUtensorMap* tmC, const CUtensorMap* tmZ) {
+  constexpr int NCH = BN / 64;
+  const int M = cx.M;
+  const int lane = cx.lane;
+  const unsigned long long seed = ep.drop_p > 0.0f ? eff_seed(ep.drop_seed, ep.drop_seed_ptr) : 0ull;
+  const float keep = ep.drop_p > 0.0f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+  const uint32_t thr16 = drop_thr16(ep.drop_p);
+  uint8_t* obuf = reinterpret_cast<uint8_t*>(cx.patch);     // 2 KB out tile
+  uint8_t* zbuf = obuf + 2048;                               // 2 KB pre-activation tile (GELU)
+  const T* aux = reinterpret_cast<const T*>(ep.aux_in);
+
+  auto load_aux = [&](int m, int nc, uint4 (&a)[4]) {
+    if (MODE == EPI_DGELU && m < M) {
+      const uint4* src = reinterpret_cast<const uint4*>(aux + (size_t)m * ep.ldaux + nc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = __ldg(src + q);
+    }
+  };
+
+  int local = 0;
+  int m0 = 0, n0 = 0, kb0 = 0, kb1 = 0;
+  uint4 cur_aux[4] = {};
+  int t = cx.cluster_id;
+  if (t < sc.num_tiles) {
+    tile_coords2<BN>(sc, t, m0, n0, kb0, kb1);
+    load_aux(m0 + cx.row_off + lane, n0 + cx.col_off, cur_aux);
+  }
+  for (; t < sc.num_tiles; t += cx.num_clusters, ++local) {
+    const int buf = local & 1;
+    const int mrow0 = m0 + cx.row_off;
+    const int m = mrow0 + lane;
+    int nm0 = 0, nn0 = 0, nkb0 = 0, nkb1 = 0;
+    const bool has_next = t + cx.num_clusters < sc.num_tiles;
+    if (has_next) tile_coords2<BN>(sc, t + cx.num_clusters, nm0, nn0, nkb0, nkb1);
+    mbar_wait(&cx.tmem_full_bar[buf], ((uint32_t)local >> 1) & 1);
+    tcgen05_fence_after();
+    const uint32_t tacc = cx.tmem_base + (uint32_t)(buf * BN + cx.col_off) + ((uint32_t)(cx.lg * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int nc = n0 + cx.col_off + c * 32;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tacc + (uint32_t)(c * 32), r);
+      uint4 nxt_aux[4] = {};
+      if (c + 1 < NCH) load_aux(m, nc + 32, nxt_aux);
+      else if (has_next) load_aux(nm0 + cx.row_off + lane, nn0 + cx.col_off, nxt_aux);
+      tmem_ld_wait();
+      if (c == NCH - 1) {
+        tcgen05_fence_before();
+        if (lane == 0) mbar_arrive_cluster(buf ? cx.release_bar1 : cx.release_bar0);
+      }
+      // the previous patch's TMA stores must have finished READING the staging tiles before they are rewritten
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {          // 8 columns per 16-byte chunk
+        float v[8];
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (MODE != EPI_DGELU && ep.bias) {
+          b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + q * 8));
+          b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + q * 8 + 4));
+        }
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[q * 8 + j]), ep.alpha, bb[j]);
+        if constexpr (MODE == EPI_GELU) {
+          uint4 z;
+          z.x = pack2<T>(v[0], v[1]); z.y = pack2<T>(v[2], v[3]); z.z = pack2<T>(v[4], v[5]); z.w = pack2<T>(v[6], v[7]);
+          *reinterpret_cast<uint4*>(sw64_chunk(zbuf, lane, q)) = z;
+          // GELU of the ROUNDED pre-activation: backward only ever sees the stored 16-bit z
+          const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<T>(zw[j]);
+            v[2 * j] = gelu_fast(f.x);
+            v[2 * j + 1] = gelu_fast(f.y);
+          }
+        }
+        if constexpr (MODE == EPI_DGELU) {
+          const uint32_t aw[4] = {cur_aux[q].x, cur_aux[q].y, cur_aux[q].z, cur_aux[q].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<T>(aw[j]);
+            v[2 * j] *= dgelu_fast(f.x);
+            v[2 * j + 1] *= dgelu_fast(f.y);
+          }
+        }
+        if constexpr (MODE != EPI_T16) {
+          if (ep.drop_p > 0.0f) {
+            const unsigned long long idx = (unsigned long long)(m + ep.drop_row0) * (unsigned long long)ep.ldc + nc + q * 8;
+            float lo4[4] = {v[0], v[1], v[2], v[3]}, hi4[4] = {v[4], v[5], v[6], v[7]};
+            drop_apply4(lo4, seed, idx, thr16, keep);
+            drop_apply4(hi4, seed, idx + 4, thr16, keep);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[j] = lo4[j]; v[4 + j] = hi4[j]; }
+          }
+        }
+        uint4 w;
+        w.x = pack2<T>(v[0], v[1]); w.y = pack2<T>(v[2], v[3]); w.z = pack2<T>(v[4], v[5]); w.w = pack2<T>(v[6], v[7]);
+        *reinterpret_cast<uint4*>(sw64_chunk(obuf, lane, q)) = w;
+      }
+      fence_proxy_async();        // the generic-proxy writes above become visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, obuf, nc, mrow0);
+        if (MODE == EPI_GELU) tma_store_2d(tmZ, zbuf, nc, mrow0);
+        bulk_commit();
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cur_aux[q] = nxt_aux[q];
+    }
+    m0 = nm0; n0 = nn0; kb0 = nkb0; kb1 = nkb1;
+  }
+  if (lane == 0) bulk_wait_all();   // the staging tiles (and this CTA's shared memory) must outlive the last store
+  __syncwarp();
+}
+
 template <typename T, int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmB2, EpiParams ep, int M, int N, int K, Sched2 sc, int epi_mode) {
+                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmC,
+                  const __grid_constant__ CUtensorMap tmZ, EpiParams ep, int M, int N, int K, Sched2 sc, int epi_mode) {
   static_assert(BN == 128 || BN == 256, "pair tile is 256 x 128 or 256 x 256");
   using C = Cfg2<BN, STAGES>;
   constexpr int BNH = BN / 2;       // B rows staged by each CTA
@@ -359,6 +503,10 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (sc.kb_wrap > 0) tma_prefetch_desc(&tmB2);
+    if (epi_mode >= EPI_T16_TMA) {
+      tma_prefetch_desc(&tmC);
+      if (epi_mode == EPI_GELU_TMA) tma_prefetch_desc(&tmZ);
+    }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);    // the leader's producer (arrive.expect_tx of both CTAs' bytes)
@@ -474,6 +622,9 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       case EPI_GELU: epilogue_loop<T, BN, EPI_GELU>(ep, sc, cx); break;
       case EPI_DGELU: epilogue_loop<T, BN, EPI_DGELU>(ep, sc, cx); break;
       case EPI_RES32: epilogue_loop<T, BN, EPI_RES32>(ep, sc, cx); break;
+      case EPI_T16_TMA: epilogue_loop_tma<T, BN, EPI_T16>(ep, sc, cx, &tmC, &tmZ); break;
+      case EPI_GELU_TMA: epilogue_loop_tma<T, BN, EPI_GELU>(ep, sc, cx, &tmC, &tmZ); break;
+      case EPI_DGELU_TMA: epilogue_loop_tma<T, BN, EPI_DGELU>(ep, sc, cx, &tmC, &tmZ); break;
       default: epilogue_loop<T, BN, EPI_GENERIC>(ep, sc, cx); break;
     }
   }
@@ -495,6 +646,21 @@ int epi_mode_of(const EpiParams& ep) {
   if (ep.act == GOAT_ACT_GELU && ep.aux_out) return EPI_GELU;
   if (ep.act == GOAT_ACT_DGELU && ep.aux_in && !ep.bias) return EPI_DGELU;
   return EPI_GENERIC;
+}
+
+// 16-bit output modes take the TMA-store epilogue when the output (and the GELU pre-activation copy) can be described
+// by a tensor map: 16-byte aligned base, leading dimension a multiple of 8 elements, N a multiple of the 32-column patch
+int epi_mode_tma(int mode, const goat_gemm_args& a, const EpiParams& ep) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GOAT_GEMM_TMA_STORE");
+    on = (e && *e == '0') ? 0 : 1;
+  }
+  if (!on || (mode != EPI_T16 && mode != EPI_GELU && mode != EPI_DGELU)) return mode;
+  if ((a.N & 31) || (ep.ldc & 7) || !aligned16(ep.out)) return mode;
+  if (mode == EPI_GELU && ((ep.ldaux & 7) || !aligned16(ep.aux_out))) return mode;
+  if (mode == EPI_DGELU && ((ep.ldaux & 7) || !aligned16(ep.aux_in))) return mode;
+  return mode == EPI_T16 ? EPI_T16_TMA : mode == EPI_GELU ? EPI_GELU_TMA : EPI_DGELU_TMA;
 }
 
 template <typename T, int BN, int STAGES, bool A_MN, bool B_MN>
@@ -549,8 +715,14 @@ int launch2(const goat_gemm_args& a, const EpiParams& ep, cudaStream_t stream) {
   sc.splits = (sc.num_kb + sc.kb_per_split - 1) / sc.kb_per_split;   // no empty splits
   sc.num_tiles = mn * sc.splits;
   const int clusters = sc.num_tiles < pairs ? sc.num_tiles : pairs;
-  GOAT_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmB2, ep, a.M, a.N, a.K, sc,
-                       epi_mode_of(ep)));
+  const int mode = epi_mode_tma(epi_mode_of(ep), a, ep);
+  CUtensorMap tmC = tmA, tmZ = tmA;
+  if (mode >= EPI_T16_TMA) {
+    if ((rc = make_tmap_sw64(&tmC, a.dtype, ep.out, a.N, a.M, ep.ldc, 32, 32))) return rc;
+    if (mode == EPI_GELU_TMA && (rc = make_tmap_sw64(&tmZ, a.dtype, ep.aux_out, a.N, a.M, ep.ldaux, 32, 32))) return rc;
+  }
+  GOAT_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmB2, tmC, tmZ, ep, a.M, a.N,
+                       a.K, sc, mode));
   return GOAT_OK;
 }
 
