@@ -6,7 +6,7 @@ import torch
 from vln_goat_b200 import ops
 
 dev = "cuda"
-dt = torch.bfloat16
+dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("DT", "fp16")]
 reps = int(os.environ.get("REPS", "20"))
 warm = int(os.environ.get("WARM", "3"))
 
@@ -55,10 +55,19 @@ M = 5120
 x = torch.randn(M, 768, device=dev).to(dt)
 x32 = torch.randn(M, 768, device=dev)
 h = torch.randn(M, 3072, device=dev).to(dt)
-Wqkv = (torch.randn(2304, 768, device=dev) * 0.02).to(dt)
-Wo = (torch.randn(768, 768, device=dev) * 0.02).to(dt)
-W1 = (torch.randn(3072, 768, device=dev) * 0.02).to(dt)
-W2 = (torch.randn(768, 3072, device=dev) * 0.02).to(dt)
+def _w(n, k):
+    """a weight operand; SPLIT=1: a [hi | lo] split weight (forward GEMMs then run the K loop twice, runtime.py)"""
+    w32 = torch.randn(n, k, device=dev) * 0.02
+    if os.environ.get("SPLIT", "0") == "1":
+        from vln_goat_b200 import runtime
+        return runtime._cast_split(w32, dt)
+    return w32.to(dt)
+
+
+Wqkv = _w(2304, 768)
+Wo = _w(768, 768)
+W1 = _w(3072, 768)
+W2 = _w(768, 3072)
 b3 = torch.zeros(2304, device=dev); b1 = torch.zeros(3072, device=dev); b0 = torch.zeros(768, device=dev)
 z = torch.empty(M, 3072, device=dev, dtype=dt)
 dy = torch.randn(M, 768, device=dev).to(dt)
@@ -115,6 +124,18 @@ if which in ("all", "attn"):
     qc = torch.randn(B, Nq, 768, device=dev).to(dt)
     kv = torch.randn(B, L, 1536, device=dev).to(dt)
     timeit("attn fwd cross B64 Nq37 Nk80", lambda: ops.attn_fwd(qc, kv[:, :, :768], kv[:, :, 768:], 12, km))
+if which in ("all", "attnlong"):
+    # BASELINE.json configs[4]: text self-attention of the 512-token stress (query-tiled kernels of attention_tc.cu)
+    B, L = 32, 512
+    qkv = torch.randn(B, L, 2304, device=dev).to(dt)
+    q, k, v = qkv[:, :, :768], qkv[:, :, 768:1536], qkv[:, :, 1536:]
+    km = torch.zeros(B, L, device=dev)
+    w = torch.randn(B, L, 768, device=dev).to(dt)
+    dq = torch.empty_like(qkv)
+    o, lse = ops.attn_fwd(q, k, v, 12, km, drop_p=0.1, drop_seed=3)
+    nbytes = 4 * B * L * 768 * 2
+    timeit("attn fwd self B32 L512 p=0.1", lambda: ops.attn_fwd(q, k, v, 12, km, drop_p=0.1, drop_seed=3), 4 * B * 12 * L * L * 64, nbytes)
+    timeit("attn bwd self B32 L512 p=0.1", lambda: ops.attn_bwd(w, q, k, v, o, lse, 12, dq[:, :, :768], dq[:, :, 768:1536], dq[:, :, 1536:], km, drop_p=0.1, drop_seed=3), 10 * B * 12 * L * L * 64, 2 * nbytes)
 if which in ("all", "misc"):
     g = torch.ones(768, device=dev); bt = torch.zeros(768, device=dev)
     y32, y16, mean, rstd = ops.layernorm_fwd(x32, g, bt, 1e-12, True, dt)
