@@ -21,7 +21,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "attn_common.cuh"
 
 namespace goat {
 
@@ -30,12 +30,11 @@ int make_tmap3(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64
 
 namespace {
 
+using namespace attn;
+
 constexpr int TC_THREADS = 128;
 constexpr int KC = 128;               // keys per chunk
-constexpr int TILE = 128 * 128;       // bytes of a [128 rows][64 x 2 B] tile
 constexpr int TMEM_COLS = 256;
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
 
 struct TcArgs {
   int B, heads, Nq, Nk;
@@ -54,32 +53,6 @@ struct TcArgs {
   float* dbias;
 };
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-// address of 16-byte chunk `q` (8 elements) of row `r` inside a [rows][64] 128B-swizzled tile
-__device__ __forceinline__ uint8_t* sw_chunk(uint8_t* tile, int r, int q) { return tile + r * 128 + ((q ^ (r & 7)) << 4); }
-
-// store 32 consecutive fp32 values (columns c0 .. c0+31 of row r) as 16-bit into the [2 blocks][128 rows][64] operand
-template <typename T>
-__device__ __forceinline__ void store_row32(uint8_t* buf, int r, int c0, const float (&v)[32]) {
-  uint8_t* tile = buf + (c0 >> 6) * TILE;
-  const int q0 = (c0 & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 w;
-    w.x = pack2<T>(v[q * 8 + 0], v[q * 8 + 1]);
-    w.y = pack2<T>(v[q * 8 + 2], v[q * 8 + 3]);
-    w.z = pack2<T>(v[q * 8 + 4], v[q * 8 + 5]);
-    w.w = pack2<T>(v[q * 8 + 6], v[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(sw_chunk(tile, r, q0 + q)) = w;
-  }
-}
-
 // write 64 fp32 values as one 128-byte row of 16-bit elements to global memory
 template <typename T>
 __device__ __forceinline__ void store_global_row64(T* dst, const float* v, float mul) {
@@ -93,11 +66,6 @@ __device__ __forceinline__ void store_global_row64(T* dst, const float* v, float
     w.w = pack2<T>(v[q * 8 + 6] * mul, v[q * 8 + 7] * mul);
     d[q] = w;
   }
-}
-
-__device__ __forceinline__ float drop_mul(const TcArgs& p, unsigned long long seed, int b, int h, int qi, int kj) {
-  const uint32_t rowkey = attn_drop_rowkey(seed, b, p.heads, h, p.Nq, qi);
-  return attn_drop_keep(rowkey, kj, drop_thr16(p.drop_p)) ? 1.f / (1.f - p.drop_p) : 0.f;
 }
 
 struct Smem {
@@ -168,15 +136,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                k ? 1u : 0u);
   };
   const float sl2 = p.scale * LOG2E;
-  // log2-domain score of chunk-local key j (global key `key`): masked / out-of-range keys come out as -inf via kml
-  auto score = [&](float acc, int j, int key) -> float {
-    float s = fmaf(acc, sl2, kml[j]);
-    if (brow && key < p.Nk) s = fmaf(__ldg(brow + key), LOG2E, s);
-    return s;
-  };
+  const bool drop = p.drop_p > 0.f;
+  const uint32_t thr16 = drop_thr16(p.drop_p);
+  const float keep_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint32_t rowkey = drop ? attn_drop_rowkey(seed, b, p.heads, h, p.Nq, r) : 0u;
   auto fill_kml = [&](int c) {
     const int key = c * KC + tid;
     kml[tid] = key < p.Nk ? (krow ? __ldg(krow + key) * LOG2E : 0.f) : -INFINITY;
+  };
+  // Branch-free 16-key blocks (same arithmetic as attention_pipe.cu): masked / out-of-range keys carry -inf in the staged
+  // mask; rows past Nq see zero-filled Q rows (S = 0) and are never stored.  One hash per key PAIR for dropout, the per-row
+  // key hoisted -- the per-element lambdas this replaces were ~40 dependent instructions per score on ONE warp per scheduler.
+  auto block_max = [&](int c, int nk16, float mm) -> float {
+#pragma unroll 1
+    for (int kb = 0; kb * 16 < nk16; ++kb) {
+      uint32_t rr[16];
+      float kv[16];
+      tmem_ld_32x32b_x16(t_row + kb * 16, rr);
+      load_kv16c(kml, brow, kb * 16, c * KC + kb * 16, p.Nk, kv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mm = fmaxf(mm, fmaf(__uint_as_float(rr[j]), sl2, kv[j]));
+    }
+    return mm;
   };
 
   // ---- pass A (only when the keys do not fit one chunk): exact row maxima
@@ -198,18 +180,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ph_mma ^= 1;
       tcgen05_fence_after();
       __syncthreads();
-      if (warp_live) {
-        for (int g = 0; g * 32 < nk; ++g) {
-          uint32_t rr[32];
-          tmem_ld_32x32b_x32(t_row + g * 32, rr);
-          tmem_ld_wait();
-          if (rv) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * KC + g * 32 + j < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), g * 32 + j, c * KC + g * 32 + j));
-          }
-        }
-      }
+      if (warp_live) m = block_max(c, nk16, m);
       tcgen05_fence_before();
       __syncthreads();
     }
@@ -235,36 +206,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_after();
     __syncthreads();
     if (warp_live) {
-      if (nchunks == 1) {
-        for (int g = 0; g * 32 < nk; ++g) {
-          uint32_t rr[32];
-          tmem_ld_32x32b_x32(t_row + g * 32, rr);
-          tmem_ld_wait();
-          if (rv) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (g * 32 + j < p.Nk) m = fmaxf(m, score(__uint_as_float(rr[j]), g * 32 + j, g * 32 + j));
-          }
-        }
-      }
+      if (nchunks == 1) m = block_max(c, nk16, m);
       const float mref = (m == -INFINITY) ? 0.f : m;
-      for (int g = 0; g * 32 < nk16; ++g) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(t_row + g * 32, rr);
+#pragma unroll 1
+      for (int kb = 0; kb * 16 < nk16; ++kb) {
+        uint32_t rr[16];
+        float kv[16], pv[16];
+        tmem_ld_32x32b_x16(t_row + kb * 16, rr);
+        load_kv16c(kml, brow, kb * 16, c * KC + kb * 16, p.Nk, kv);
         tmem_ld_wait();
-        float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c * KC + g * 32 + j;
-          float e = 0.f;
-          if (rv && key < p.Nk) {   // TMEM columns past the MMA's N hold stale data (possibly NaN): never touch them
-            e = ex2_approx(score(__uint_as_float(rr[j]), g * 32 + j, key) - mref);
-            l += e;
-            if (p.drop_p > 0.f) e *= drop_mul(p, seed, b, h, r, key);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float e = ex2_approx(fmaf(__uint_as_float(rr[j]), sl2, kv[j]) - mref);
+          l += e;
           pv[j] = e;
         }
-        store_row32<T>(sP, tid, g * 32, pv);
+        if (drop) drop_mul16(pv, rowkey, c * KC + kb * 16, thr16, keep_scale);
+        store_row16<T>(sP, tid, kb * 16, pv);
       }
     }
     fence_proxy_async();
@@ -383,6 +341,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     lse = p.lse[((long long)b * p.heads + h) * p.Nq + r] * LOG2E;
   }
   const float sl2 = p.scale * LOG2E;
+  const bool drop = p.drop_p > 0.f;
+  const uint32_t thr16 = drop_thr16(p.drop_p);
+  const float keep_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint32_t rowkey = drop ? attn_drop_rowkey(seed, b, p.heads, h, p.Nq, r) : 0u;
+  if (lse == -INFINITY) lse = INFINITY;     // a fully masked row: every probability exp2(s - inf) = 0 instead of NaN
   float dq[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) dq[j] = 0.f;
@@ -419,30 +382,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_after();
     __syncthreads();
 
-    for (int g = 0; g * 32 < nk16; ++g) {
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32b_x32(t_row + g * 32, rs);
-      tmem_ld_32x32b_x32(t_row + 128 + g * 32, rp);
+    // one branch-free pass over 16-key blocks: P = exp2(S - lse), P~ = dropout(P), dS = P~ dP - P delta (rows past Nq see
+    // zero-filled Q / dO rows: finite P, dP = 0, delta = 0)
+#pragma unroll 1
+    for (int kb = 0; kb * 16 < nk16; ++kb) {
+      uint32_t rs[16], rp[16];
+      float kv[16], pt[16], ds[16];
+      tmem_ld_32x32b_x16(t_row + kb * 16, rs);
+      tmem_ld_32x32b_x16(t_row + 128 + kb * 16, rp);
+      load_kv16c(kml, brow, kb * 16, c * KC + kb * 16, p.Nk, kv);
       tmem_ld_wait();
-      float pv[32], dsv[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = c * KC + g * 32 + j;
-        float pd = 0.f, ds = 0.f;
-        if (rv && key < p.Nk) {
-          float s = fmaf(__uint_as_float(rs[j]), sl2, kml[g * 32 + j]);
-          if (brow) s = fmaf(__ldg(brow + key), LOG2E, s);
-          const float pr = ex2_approx(s - lse);
-          const float dm = p.drop_p > 0.f ? drop_mul(p, seed, b, h, r, key) : 1.f;
-          pd = pr * dm;
-          ds = pr * (__uint_as_float(rp[j]) * dm - delta);
-          if (dbrow) atomicAdd(dbrow + key, ds);
-        }
-        pv[j] = pd;
-        dsv[j] = ds;
+      for (int j = 0; j < 16; ++j) {
+        const float pr = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, kv[j]) - lse);
+        pt[j] = pr;
+        ds[j] = -pr * delta;
       }
-      if (KV_OUT) store_row32<T>(sP, tid, g * 32, pv);
-      store_row32<T>(sdS, tid, g * 32, dsv);
+      if (drop) drop_mul16(pt, rowkey, c * KC + kb * 16, thr16, keep_scale);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ds[j] = fmaf(pt[j], __uint_as_float(rp[j]), ds[j]);
+      if (dbrow && rv) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c * KC + kb * 16 + j < p.Nk) atomicAdd(dbrow + c * KC + kb * 16 + j, ds[j]);
+      }
+      if (KV_OUT) store_row16<T>(sP, tid, kb * 16, pt);
+      store_row16<T>(sdS, tid, kb * 16, ds);
     }
     fence_proxy_async();
     tcgen05_fence_before();
@@ -564,6 +529,9 @@ attn_bwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   const unsigned long long seed = p.drop_p > 0.f ? eff_seed(p.drop_seed, p.drop_seed_ptr) : 0ull;
   const float sl2 = p.scale * LOG2E;
+  const bool drop = p.drop_p > 0.f;
+  const uint32_t thr16 = drop_thr16(p.drop_p);
+  const float keep_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
   const int nqt = (p.Nq + 127) / 128;
   uint32_t ph_q = 0, ph_mma = 0;
   for (int qt = 0; qt < nqt; ++qt) {
@@ -593,6 +561,7 @@ attn_bwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         x = unpack2<T>(a.w); y = unpack2<T>(g.w); delta += x.x * y.x + x.y * y.y;
       }
       lse = p.lse[((long long)b * p.heads + h) * p.Nq + r] * LOG2E;
+      if (lse == -INFINITY) lse = INFINITY;
     }
     if (tid == 0) {
       if (qt == 0) mbar_wait(bar_kv, 0);
@@ -615,29 +584,25 @@ attn_bwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ph_mma ^= 1;
     tcgen05_fence_after();
     __syncthreads();     // kml visible (first tile)
-    for (int g = 0; g * 32 < nk16; ++g) {
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32b_x32(t_row + COL_S + g * 32, rs);
-      tmem_ld_32x32b_x32(t_row + COL_DP + g * 32, rp);
+#pragma unroll 1
+    for (int kb = 0; kb * 16 < nk16; ++kb) {
+      uint32_t rs[16], rp[16];
+      float kv[16], pt[16], ds[16];
+      tmem_ld_32x32b_x16(t_row + COL_S + kb * 16, rs);
+      tmem_ld_32x32b_x16(t_row + COL_DP + kb * 16, rp);
+      load_kv16c(kml, brow, kb * 16, c * KC + kb * 16, p.Nk, kv);
       tmem_ld_wait();
-      float pv[32], dsv[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = c * KC + g * 32 + j;
-        float pd = 0.f, ds = 0.f;
-        if (rv && key < p.Nk) {
-          float s = fmaf(__uint_as_float(rs[j]), sl2, kml[g * 32 + j]);
-          if (brow) s = fmaf(__ldg(brow + key), LOG2E, s);
-          const float pr = ex2_approx(s - lse);
-          const float dm = p.drop_p > 0.f ? drop_mul(p, seed, b, h, r, key) : 1.f;
-          pd = pr * dm;
-          ds = pr * (__uint_as_float(rp[j]) * dm - delta);
-        }
-        pv[j] = pd;
-        dsv[j] = ds;
+      for (int j = 0; j < 16; ++j) {
+        const float pr = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, kv[j]) - lse);
+        pt[j] = pr;
+        ds[j] = -pr * delta;
       }
-      store_row32<T>(sP, tid, g * 32, pv);
-      store_row32<T>(sdS, tid, g * 32, dsv);
+      if (drop) drop_mul16(pt, attn_drop_rowkey(seed, b, p.heads, h, p.Nq, r), c * KC + kb * 16, thr16, keep_scale);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ds[j] = fmaf(pt[j], __uint_as_float(rp[j]), ds[j]);
+      store_row16<T>(sP, tid, kb * 16, pt);
+      store_row16<T>(sdS, tid, kb * 16, ds);
     }
     fence_proxy_async();
     tcgen05_fence_before();
