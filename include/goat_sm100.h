@@ -296,6 +296,12 @@ int goat_embed_fwd(const long long* ids, const float* word, const float* pos, co
 int goat_embed_bwd(const float* dout, const long long* ids, int M, int L, int H, long long padding_idx, float* dword,
                    float* dpos, float* dtype, goat_stream_t stream);
 
+/* GPU-resident feature bank: the reference reads the pre-extracted 36-view CLIP/ViT features of every
+ * trajectory step from HDF5 on the host and copies [S,36,768] fp32 to the device per batch (P/data/dataset.py:811-818,
+ * P/data/loader.py:78-87).  Here the whole table lives in HBM once, in 16 bit, and a batch carries one int per step:
+ * out[r, :] = src[idx[r], :] over rows of row_bytes (a multiple of 16) bytes; idx < 0 gives a zero row (padded steps). */
+int goat_gather_rows(const void* src, const int* idx, int R, long long row_bytes, void* out, goat_stream_t stream);
+
 /* Backward of the activation behind a head / pooler nn.Linear (ClsPrediction ReLU, BertPooler tanh, the GELU of the
  * MLM / CFP transforms: P/model/pretrain_goat.py:27-38, P/model/Bert_backbone.py:783-811):
  *   out[i] = dy[i] * act'(ref[i]) converted to out_dtype, one pass.  ref = the forward OUTPUT y (fp32) for RELU / TANH

@@ -607,3 +607,31 @@ def test_chunked_vocab_cross_entropy_matches_materialised_logits(dtype):
     ftol = 2e-5 if dtype == torch.float32 else 2e-3
     assert _rel(outs[0][0], ref.detach()) < ftol
     assert (outs[0][1] - xr.grad).abs().max().item() <= (ftol * 5) * max(1e-6, xr.grad.abs().max().item())
+
+
+def test_feature_bank_path_equals_host_features():
+    """batches that name their panoramas by row of a GPU-resident 16-bit workloads.FeatureBank give exactly
+    the outputs of batches that carry the (16-bit representable) features themselves."""
+    from vln_goat_b200 import batching, runtime, workloads
+    model = _pretrain_model()
+    batch = synth.pretrain_batch(B=3, L=24, seed=5)
+    batch["traj_view_img_fts"] = batch["traj_view_img_fts"].half().float()
+    S = batch["traj_view_img_fts"].shape[0]
+    g = torch.Generator().manual_seed(1)
+    perm = torch.randperm(S + 5, generator=g)[:S]
+    table = torch.zeros(S + 5, 36, 768)
+    table[perm] = batch["traj_view_img_fts"]
+    model.bert.feature_bank = workloads.FeatureBank(table, dtype=torch.float16)
+    b2 = {k: v for k, v in batch.items() if k != "traj_view_img_fts"}
+    b2["traj_view_ids"] = perm.to(torch.int32)
+    pad = batching.PadSpec(S=8, G=8, NM=16)
+    with runtime.compute(torch.float16), torch.no_grad():
+        for task in ("sap", "cfp"):
+            P0 = synth.batch_to(batching.prepare_pretrain(batch, task, pad=pad), "cuda")
+            P1 = synth.batch_to(batching.prepare_pretrain(b2, task, pad=pad), "cuda")
+            assert "view_idx" in P1 and "view_fts" not in P1 and int(P1["view_idx"][-1]) == -1
+            a = model.forward_prepared(P0, task, compute_loss=False)
+            b = model.forward_prepared(P1, task, compute_loss=False)
+            for x, y in zip(a, b):
+                if torch.is_floating_point(x):
+                    assert torch.equal(x, y)

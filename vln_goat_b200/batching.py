@@ -74,12 +74,13 @@ def prepare_pretrain(batch, task, pad=None, pano_fusion=True, pinned=False):
         raise NotImplementedError("task %r is outside the hot-path scope (MRC / OG are REVERIE-only)" % task)
     if batch.get("traj_obj_img_fts") is not None:
         raise NotImplementedError("object features (REVERIE / SOON) are outside the hot-path scope")
-    feats = batch["traj_view_img_fts"]
-    dev = feats.device
+    view_ids = batch.get("traj_view_ids")          # rows of a GPU-resident workloads.FeatureBank instead of the features
+    feats = batch.get("traj_view_img_fts")
+    dev = (feats if feats is not None else batch["traj_loc_fts"]).device
     step_lens = [int(x) for x in batch["traj_step_lens"]]
     B = len(step_lens)
     S = sum(step_lens)
-    V = feats.shape[1]
+    V = feats.shape[1] if feats is not None else batch["traj_loc_fts"].shape[1]
     view_lens = batch["traj_vp_view_lens"]
     view_lens_h = _cpu(view_lens).tolist()
     gmap_step_ids = batch["gmap_step_ids"]
@@ -116,7 +117,7 @@ def prepare_pretrain(batch, task, pad=None, pano_fusion=True, pinned=False):
         raise ValueError("the batch has %d tokens per instruction, more than the padded length %d" % (L, Lp))
     out = {
         "txt_ids": _pad_dim1(txt_ids, Lp), "txt_lens": batch["txt_lens"],
-        "view_fts": _pad_dim0(feats, Sp, 0, pinned), "loc_fts": _pad_dim0(batch["traj_loc_fts"], Sp, 0, pinned),
+        "loc_fts": _pad_dim0(batch["traj_loc_fts"], Sp, 0, pinned),
         "view_lens": _pad_dim0(view_lens, Sp, 1), "last_rows": put(last_rows),
         "gmap_idx_f": put(idx_f.contiguous()), "gmap_idx_v": put(idx_v.contiguous()),
         "gmap_step_ids": _pad_dim1(gmap_step_ids, Gp), "gmap_pos_fts": _pad_dim1(batch["gmap_pos_fts"], Gp),
@@ -124,6 +125,10 @@ def prepare_pretrain(batch, task, pad=None, pano_fusion=True, pinned=False):
         "n_gmap": put(torch.tensor([Gn], dtype=torch.int32)), "n_vp": put(torch.tensor([Nq], dtype=torch.int32)),
         "n_txt": put(torch.tensor([L], dtype=torch.int32)),
     }
+    if view_ids is not None:
+        out["view_idx"] = _pad_dim0(view_ids.to(torch.int32), Sp, -1)
+    else:
+        out["view_fts"] = _pad_dim0(feats, Sp, 0, pinned)
     for k in _Z_KEYS:
         if batch.get(k) is not None:
             out[k] = batch[k]

@@ -419,6 +419,17 @@ __global__ void act_grad_kernel(const float* __restrict__ dy, const R* __restric
   }
 }
 
+// rows of 16-byte words gathered by index (feature bank: panorama rows of 36 x 768 16-bit features); idx < 0 -> zero row
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, long long words_per_row,
+                                   uint4* __restrict__ out) {
+  const int r = blockIdx.y;
+  const long long s = idx[r];
+  const uint4* srow = src + s * words_per_row;
+  uint4* orow = out + (long long)r * words_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_row; i += (long long)gridDim.x * blockDim.x)
+    orow[i] = s >= 0 ? __ldg(srow + i) : make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void act_fwd_kernel(const float* __restrict__ x, int act, float* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -624,6 +635,21 @@ int goat_act_grad(const float* dy, const void* ref, int ref_dtype, int act, void
   if (ref_dtype == GOAT_F16) return act_grad_launch<__half>(dy, ref, act, out, out_dtype, n, st);
   if (ref_dtype == GOAT_BF16) return act_grad_launch<__nv_bfloat16>(dy, ref, act, out, out_dtype, n, st);
   GOAT_CHECK(false, "goat_act_grad: bad ref dtype");
+}
+
+int goat_gather_rows(const void* src, const int* idx, int R, long long row_bytes, void* out, goat_stream_t stream) {
+  GOAT_CHECK(src && idx && out, "goat_gather_rows: null argument");
+  GOAT_CHECK(row_bytes > 0 && (row_bytes & 15) == 0 && aligned16(src) && aligned16(out),
+             "goat_gather_rows: rows must be multiples of 16 bytes and 16-byte aligned");
+  if (R <= 0) return GOAT_OK;
+  GOAT_CHECK(R <= 65535, "goat_gather_rows: too many rows");
+  const long long words = row_bytes / 16;
+  int gx = (int)((words + 255) / 256);
+  if (gx > 16) gx = 16;
+  gather_rows_kernel<<<dim3(gx, R), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(src), idx, words, reinterpret_cast<uint4*>(out));
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
 }
 
 int goat_act_fwd(const float* x, int act, float* out, long long n, goat_stream_t stream) {

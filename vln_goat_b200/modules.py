@@ -510,9 +510,13 @@ def linear(lin, x, act=ops.ACT_NONE):
     """act(x W^T + b) on [.., in] fp32 -> [.., out] fp32 through goat_gemm."""
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
+    cdt = runtime.compute_dtype()
+    if x2.dtype == cdt and cdt != torch.float32 and not x2.requires_grad:
+        # already a 16-bit GEMM operand (rows gathered from the GPU-resident feature bank): no fp32 copy, no cast kernel
+        y = Fn.LinearFn.apply(None, x2.contiguous(), lin.weight, lin.bias, runtime.wc(lin.weight, cdt), act, cdt)
+        return y.view(shp[:-1] + (lin.weight.shape[0],))
     if x2.dtype != torch.float32:
         x2 = x2.float()
-    cdt = runtime.compute_dtype()
     y = Fn.LinearFn.apply(x2.contiguous(), None, lin.weight, lin.bias, runtime.wc(lin.weight, cdt), act, cdt)
     return y.view(shp[:-1] + (lin.weight.shape[0],))
 

@@ -489,6 +489,18 @@ def act_grad(dy, ref, act, out_dtype):
     return out
 
 
+def gather_rows(src, idx):
+    """src [R0, ...] (contiguous, any dtype, row size a multiple of 16 bytes), idx int32 [R] (-1 = zero row) -> [R, ...]"""
+    _req_cuda(src, idx)
+    if not src.is_contiguous() or idx.dtype != torch.int32 or idx.dim() != 1 or not idx.is_contiguous():
+        raise ValueError("gather_rows: src must be contiguous and idx a contiguous int32 vector")
+    row_bytes = (src.numel() // src.shape[0]) * src.element_size()
+    out = torch.empty((idx.shape[0],) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    _lib.check(_lib.lib().goat_gather_rows(_p(src), _p(idx), idx.shape[0], row_bytes, _p(out), _stream()), "goat_gather_rows")
+    LAUNCHES[0] += 1
+    return out
+
+
 def act_fwd(x, act):
     """fp32 contiguous -> act(x) fp32 (exact erf GELU / ReLU / tanh)"""
     _req_cuda(x)

@@ -62,7 +62,15 @@ class GlocalTextPathCMT(nn.Module):
                                     z_landm_embeds=zl, z_landm_pzs=P.get("instr_z_landmark_pzs"))
         else:
             txt = self.lang_encoder(self.embeddings(P["txt_ids"])[0], txt_masks)
-        views, _, fused = self.img_embeddings.encode(P["view_fts"], P["loc_fts"], P["view_lens"], P.get("img_z_features"),
+        if "view_idx" in P:
+            bank = getattr(self, "feature_bank", None)
+            if bank is None:
+                raise RuntimeError("the batch names panoramas by feature-bank row (traj_view_ids) but no bank is attached: "
+                                   "set model.bert.feature_bank = workloads.FeatureBank(features)")
+            view_fts = bank.gather(P["view_idx"])
+        else:
+            view_fts = P["view_fts"]
+        views, _, fused = self.img_embeddings.encode(view_fts, P["loc_fts"], P["view_lens"], P.get("img_z_features"),
                                                      P.get("img_z_pzs"))
         return txt, txt_masks, views, fused
 

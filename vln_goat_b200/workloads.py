@@ -168,6 +168,30 @@ def synthetic_pretrain_batch(B=64, L=80, seed=0, views=36, max_steps=5, H=768):
 PRETRAIN_TASKS = ("mlm", "sap", "cfp")
 
 
+class FeatureBank(object):
+    """GPU-resident table of the pre-extracted panorama features: [num_viewpoints, views, feat] in 16 bit,
+    uploaded once (R2R: ~10.5 k viewpoints x 36 x 768 x 2 B = 580 MB of the 180 GB).  A batch then names every trajectory step
+    by one int (``traj_view_ids``, -1 for padding) instead of carrying [S, 36, 768] fp32 over PCIe; ``gather`` returns the
+    16-bit rows that ``img_linear``'s GEMM reads directly as its TMA operand.  The reference re-reads HDF5 on the host and
+    copies fp32 every batch (P/data/dataset.py:811-818, P/data/loader.py:78-87)."""
+
+    def __init__(self, features, dtype=torch.float16, device="cuda"):
+        if features.dim() != 3:
+            raise ValueError("features must be [num_viewpoints, views, feat]")
+        self.table = features.to(device=device, dtype=dtype).contiguous()
+
+    def gather(self, idx):
+        from . import ops
+        return ops.gather_rows(self.table, idx.to(torch.int32).contiguous())
+
+    def host_rows(self, idx):
+        """the same rows as fp32 host tensors (what a checker feeds the CPU oracle)"""
+        i = idx.to(torch.int64).cpu()
+        out = self.table.cpu()[i.clamp(min=0)].float()
+        out[i < 0] = 0
+        return out
+
+
 # --------------------------------------------------------------------------------------
 # C4: a teacher-forced fine-tune rollout (language once, then panorama + navigation per step; BACL + FACL inputs) with
 # the per-step layouts of M/r2r/agent.py:86-304 / M/utils/efficiency_count.py:16-109 (SURVEY.md appendix A.2)
