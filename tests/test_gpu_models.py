@@ -633,5 +633,6 @@ def test_feature_bank_path_equals_host_features():
             a = model.forward_prepared(P0, task, compute_loss=False)
             b = model.forward_prepared(P1, task, compute_loss=False)
             for x, y in zip(a, b):
-                if torch.is_floating_point(x):
-                    assert torch.equal(x, y)
+                if torch.is_floating_point(x):      # (1-wide heads add split-K partials atomically: equal to rounding noise)
+                    fin = torch.isfinite(x)
+                    assert torch.equal(fin, torch.isfinite(y)) and _rel(y[fin], x[fin].cpu()) < 2e-6
