@@ -271,3 +271,52 @@ def test_prepare_pretrain_indices_reproduce_the_reference_loops(padded):
     assert torch.allclose((gl + add)[:, :Gn], ref, atol=1e-6)
     assert float(add[:, Gn:].abs().max()) == 0.0 if Gp > Gn else True
     assert bool(P["gmap_visited_masks"][:, Gn:].all()) if Gp > Gn else True
+
+
+def test_node_embed_bank_matches_reference_graphmap_semantics():
+    """graph_map.NodeEmbedBank (index ops over (episode, node) pairs) against the reference's dict-of-[sum, count] GraphMap
+    bookkeeping, restated literally from M/models/graph_utils.py:110-121: rewrite for the visited node, accumulation for
+    candidate views (duplicates included), sum / count reads, gradients through both."""
+    from vln_goat_b200.graph_map import NodeEmbedBank
+    g = torch.Generator().manual_seed(2)
+    E, N, H = 3, 7, 16
+    bank = NodeEmbedBank(E, N, H, device="cpu")
+    ref = [dict() for _ in range(E)]
+
+    def ref_update(e, vp, emb, rewrite=False):
+        if rewrite or vp not in ref[e]:
+            ref[e][vp] = [emb, 1]
+        else:
+            ref[e][vp] = [ref[e][vp][0] + emb, ref[e][vp][1] + 1]
+    leaves = []
+    for step in range(4):
+        # candidate views: several per episode, duplicates allowed
+        ep = torch.tensor([0, 0, 1, 2, 2, 2, 0])
+        nd = torch.tensor([1 + step % 3, 2, 3, 4, 4, 5, 1 + step % 3])
+        emb = torch.randn(len(ep), H, generator=g).requires_grad_(True)
+        leaves.append(emb)
+        bank.update(ep, nd, emb)
+        for i in range(len(ep)):
+            ref_update(int(ep[i]), int(nd[i]), emb[i])
+        # visited node of every episode: rewrite
+        ve, vn = torch.arange(E), torch.tensor([step % N, (step + 1) % N, (step + 2) % N])
+        vemb = torch.randn(E, H, generator=g).requires_grad_(True)
+        leaves.append(vemb)
+        bank.update(ve, vn, vemb, rewrite=True)
+        for i in range(E):
+            ref_update(i, int(vn[i]), vemb[i], rewrite=True)
+    table = torch.full((E, N), -1, dtype=torch.int64)
+    for e in range(E):
+        for j, vp in enumerate(sorted(ref[e])):
+            table[e, j] = vp
+    got = bank.get_padded(table)
+    w = torch.randn(E, N, H, generator=g)
+    exp = torch.zeros(E, N, H)
+    for e in range(E):
+        for j, vp in enumerate(sorted(ref[e])):
+            exp[e, j] = ref[e][vp][0] / ref[e][vp][1]
+    assert torch.allclose(got, exp, atol=1e-6)
+    g1 = torch.autograd.grad((got * w).sum(), leaves, allow_unused=True)
+    g2 = torch.autograd.grad((exp * w).sum(), leaves, allow_unused=True)
+    for a, b in zip(g1, g2):
+        assert (a is None and (b is None or float(b.abs().max()) == 0)) or torch.allclose(a, b if b is not None else torch.zeros_like(a), atol=1e-6)
