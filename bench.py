@@ -325,6 +325,13 @@ def run_goat(args):
         flat.enable_loss_scale()
     ts = engine.TrainStep(flat, use_graph=not args.no_graph, check_unwritten=False, **OPT)
 
+    # parity of the benchmarked model / dtype / batch size against the CPU oracle, on the seeded parameters (before any
+    # optimizer step: the timed steps train on random labels at a constant 5e-5, which is not a state worth certifying)
+    parity_before = None
+    extras = (not args.no_extras) and world == 1      # parity / rooflines / baselines / other configs: the 1-GPU line has them
+    if extras:
+        parity_before = parity(torch, model, host[0], dev, cdt, "seeded parameters, before the timed steps")
+
     # device-resident prepared batches; one captured graph per (task, padded-shape signature)
     resident = []
     for i in range(N_BATCHES):
@@ -425,7 +432,7 @@ def run_goat(args):
     # ---- the same end-to-end loop over a GPU-resident 16-bit feature bank: a batch names its panoramas by
     #      bank row, the [S,36,768] features never cross PCIe
     bank_line = None
-    if not args.no_extras and cdt != torch.float32:
+    if extras and cdt != torch.float32:
         feats = torch.cat([b["traj_view_img_fts"] for b in host], 0)
         model.bert.feature_bank = workloads.FeatureBank(feats, dtype=cdt, device=dev)
         host_bank, off = [], 0
@@ -479,8 +486,11 @@ def run_goat(args):
         if flat.scaler is not None:
             sc = flat.scaler.cpu().tolist()
             line["config"]["loss_scale_state"] = {"scale": sc[0], "skipped_steps": sc[3], "steps_taken": sc[4]}
-        if not args.no_extras:
-            line["parity_max_err"] = parity(torch, model, host[0], dev, cdt)
+        if extras:
+            line["parity_max_err"] = parity_before
+            after = parity(torch, model, host[0], dev, cdt, "the same parameters after all optimizer steps of this run")
+            line["parity_after_training_steps"] = {"max": after["max"], "steps_taken": flat.step_count, "worst": max(
+                (k for k in after if isinstance(after[k], float) and k not in ("max", "tolerance")), key=lambda k: after[k])}
             line["roofline"] = gemm_roofline(torch, ops, ts, resident, ms / args.steps)
             line["roofline_attention"] = attention_roofline(torch, ops, ts, resident, cdt, ms / args.steps)
             if world == 1:
@@ -544,7 +554,7 @@ def selfcheck(torch, dist, model, flat, resident, dev, rank):
               file=sys.stderr)
 
 
-def parity(torch, model, batch, dev, cdt):
+def parity(torch, model, batch, dev, cdt, state):
     """Eval-mode forward of the benchmarked model (same dtype, same batch size 64) against the CPU oracle."""
     from oracle import goat_pretrain_oracle as PO
     from vln_goat_b200 import batching
@@ -584,7 +594,7 @@ def parity(torch, model, batch, dev, cdt):
     model.train()
     errs["max"] = max(errs.values())
     errs["tolerance"] = 1e-5 if cdt == torch.float32 else 1e-3
-    errs["reference"] = "oracle/goat_pretrain_oracle.py (fp32, CPU), same parameters after the timed steps, batch 64, eval mode"
+    errs["reference"] = "oracle/goat_pretrain_oracle.py (fp32, CPU), batch 64, eval mode; " + state
     return errs
 
 
