@@ -716,9 +716,20 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
             f.write("# every GEMM shape of one MLM+SAP+CFP round: total ms per round, then the launch\n")
             for tot, line in sorted(table, reverse=True):
                 f.write("%8.3f ms  %s\n" % (tot, line))
+    traffic, traffic_src = None, None
+    try:       # DRAM bytes of the same launches, from the committed ncu pass over one round (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r02m_gemm_traffic.json")) as f:
+            tj = json.load(f)
+        if abs(tj.get("gemm_launches", 0) - n_umma) <= 0.05 * n_umma:
+            traffic, traffic_src = tj["gemm_dram_bytes_per_round"], tj["source"]
+    except Exception:
+        pass
+    algo_bytes = sum(c * 2.0 * (m_ * k_ + n_ * k_ + m_ * n_) for (m_, n_, k_, *_r), c in uniq.items() if not _r[3])
     return {"bound": "tensor", "kernel": "gemm_umma2_kernel / gemm_umma_kernel (tcgen05.mma cta_group::2 + TMA; all %d tensor-core GEMM "
                                           "launches of one MLM+SAP+CFP round, each shape re-timed as 20 graph-captured launches)" % n_umma,
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_unit": "DRAM bytes per round over the same launches", "traffic_source": traffic_src,
+            "operand_bytes_per_round": algo_bytes,
             "peak_source": which, "flop_per_round": umma_flop, "gemm_ms_per_round": umma_ms, "simt_gemm_ms_per_round": simt_ms,
             "split_weight_launches": n_split,
             "split_weight_note": ("forward GEMMs run the K loop twice (16-bit weight hi + lo terms, ~22-bit weights) for parity; "
