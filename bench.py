@@ -64,8 +64,10 @@ def parse():
                     help="plain 16-bit weight operands in the forward GEMMs (faster, ~1.6x the forward error)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip parity / rooflines / baselines / C2 (profiling runs)")
-    ap.add_argument("--selfcheck", action="store_true",
-                    help="N>1: assert bit-identical parameters and forward outputs across ranks after sharded steps")
+    ap.add_argument("--selfcheck", action="store_true", help="(default at N>1; kept for old command lines)")
+    ap.add_argument("--no-selfcheck", action="store_true",
+                    help="N>1: skip the check of bit-identical parameters / equal forward outputs across ranks after the "
+                         "timed data-parallel steps (runs outside the timed region)")
     return ap.parse_args()
 
 
@@ -456,8 +458,22 @@ def run_goat(args):
         sustained = {"steps": n_s, "seconds": ms_s / 1e3, "value": world * n_s / (ms_s / 1e3), "unit": "steps/s"}
     clk = clocks.stop() if rank == 0 else None
 
-    if args.selfcheck and world > 1:
-        selfcheck(torch, dist, model, flat, resident, dev, rank)
+    if os.environ.get("GOAT_SHARD_TIMING") and world > 1:      # diagnostic, outside every timed region
+        flat.profile_phases(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(30):
+            step_resident(i)
+        ev1.record()
+        pt = flat.phase_times()
+        flat.profile_phases(False)
+        if rank == 0 or os.environ["GOAT_SHARD_TIMING"] == "all":
+            sys.stderr.write("sharded_step phases (ms, mean of 30 steps, rank %d): %s | step %.3f ms\n"
+                             % (rank, json.dumps({k: round(v, 3) for k, v in pt.items()}), ev0.elapsed_time(ev1) / 30))
+
+    check_line = None
+    if world > 1 and not args.no_selfcheck:
+        check_line = selfcheck(torch, dist, model, flat, resident, dev, rank)
 
     if rank == 0:
         line = {
@@ -503,9 +519,16 @@ def run_goat(args):
                     line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                                             "sample": "3 timed optimizer steps (one per task MLM/SAP/CFP) at the FULL batch 64; "
                                                       "oracle/ restatement of the reference model, torch fp32, %d threads" % cores}
+        if world > 1:
+            line["selfcheck"] = check_line
+            line["config"]["gradient_exchange"] = (
+                "fused over NVLink peer memory (csrc/exchange.cu): peer loads of the gradient shards + sum of squares, clip + "
+                "AdamW on 1/world storing the new operands into every rank" if isinstance(flat._peer, dict) else
+                "NCCL reduce-scatter + AdamW on 1/world + all-gather")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        flat.release_peers()
         dist.destroy_process_group()
 
 
@@ -549,9 +572,11 @@ def selfcheck(torch, dist, model, flat, resident, dev, rank):
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if int(lo) != int(hi):
         raise RuntimeError("selfcheck: ranks hold different parameters / outputs after the data-parallel steps")
+    msg = "ok: bit-identical parameters on all %d ranks (digest %x), forward outputs equal to %.1e" % (
+        dist.get_world_size(), digest, float(wt))
     if rank == 0:
-        print("selfcheck ok: bit-identical parameters on all ranks (digest %x), forward outputs equal to %.1e" % (digest, float(wt)),
-              file=sys.stderr)
+        print("selfcheck " + msg, file=sys.stderr)
+    return msg
 
 
 def parity(torch, model, batch, dev, cdt, state):

@@ -221,6 +221,48 @@ int goat_scaler_update(float* scaler, const float* partial, int nparts, float gr
                        goat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The data-parallel gradient exchange FUSED with the optimizer step over NVLink peer memory (one process per GPU).
+ * Replaces DDP's bucketed all-reduce + a full AdamW on every rank (P/utils/misc.py:52-58, P/optim/adamw.py:64-110,
+ * P/train_r2r_goat.py:349-366).  Rank r owns elements [lo, lo+n) of the flat buffers.
+ *   goat_peer_export: CUDA IPC handle (GOAT_PEER_HANDLE_BYTES bytes) of the device allocation `ptr` lies in, and
+ *               ptr's byte offset inside it.  The allocation must be a plain cudaMalloc one (GOAT_ERR_CUDA otherwise).
+ *   goat_peer_open / goat_peer_close: map / unmap another process's allocation -> its base address in this process.
+ *               An allocation can be mapped once per process: callers cache by handle.
+ *   goat_peer_reduce_sumsq: g_shard_out[i] = sum over ranks q (in rank order) of g_peers[q][lo + i], i < n -- peer loads
+ *               through NVLink -- and partial[] = per-CTA sums of squares of the result (goat_sumsq's format).
+ *               g_peers is a HOST array of `world` device pointers (own buffer included, at index rank).
+ *               The caller must have synchronised the ranks (every rank's backward finished) before the launch.
+ *   goat_adamw_step_peers: goat_adamw_step's arithmetic on the shard (g_shard indexed from 0; m, v and p indexed by flat
+ *               element), and the new values are STORED TO EVERY RANK: shadow / shadow_lo (16-bit operand copies,
+ *               optional) for every element, the fp32 value for elements >= n_fp32_from (0: all of them); the own
+ *               rank's fp32 master is always written.  A non-finite norm with a scaler changes nothing.  The caller
+ *               synchronises the ranks again before anybody reads the buffers, and clears its own gradient buffer.
+ *   goat_peer_barrier / goat_peer_sum_scalar: rank synchronisation through flags in peer memory (one 32-thread CTA, no
+ *               NCCL call).  Every rank owns a zero-initialised signal block of goat_peer_signal_bytes() bytes;
+ *               signal_peers is the HOST array of all ranks' blocks.  `epoch` must be the same on every rank for a given
+ *               call and increase by one per call (either function).  After the barrier every rank's work enqueued before
+ *               ITS call (peer stores included) is visible to work enqueued after this one.  goat_peer_sum_scalar also
+ *               exchanges one float: out[0] = sum over ranks, in rank order, of sum(partial[0..nparts)) -- the same
+ *               bits on every rank (the global squared gradient norm).  out may alias partial.
+ *               The kernels spin until every rank arrives: all ranks must make the same sequence of calls.
+ * ------------------------------------------------------------------------------------------ */
+#define GOAT_MAX_PEERS 8
+#define GOAT_PEER_HANDLE_BYTES 64
+size_t goat_peer_signal_bytes(void);
+int goat_peer_barrier(void* const* signal_peers, int world, int rank, unsigned int epoch, goat_stream_t stream);
+int goat_peer_sum_scalar(void* const* signal_peers, int world, int rank, unsigned int epoch, const float* partial,
+                         int nparts, float* out, goat_stream_t stream);
+int goat_peer_export(const void* ptr, void* handle_out, unsigned long long* offset_out);
+int goat_peer_open(const void* handle, void** base_out);
+int goat_peer_close(void* base);
+int goat_peer_reduce_sumsq(void* const* g_peers, int world, long long lo, long long n, float* g_shard_out,
+                           float* partial, int* nparts_out, goat_stream_t stream);
+int goat_adamw_step_peers(void* const* p_peers, void* const* shadow_peers, void* const* shadow_lo_peers,
+                          int shadow_dtype, int world, int rank, const float* g_shard, float* m, float* v,
+                          long long lo, long long n, long long n_decay, long long n_fp32_from, const float* hp,
+                          const float* partial, int nparts, float* norm_out, const float* scaler, goat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Attention pooling over the token axis of x [B,N,H] (fp32), softmax WITHOUT a mask (the reference pools over
  * padding too, SURVEY.md 8a note 6).
  *   mode 0  adaptive panorama fusion  P/model/vilmodel_goat.py:354-362, M/models/vilmodel_GOAT.py:727-733:

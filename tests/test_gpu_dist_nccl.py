@@ -45,6 +45,7 @@ def _batch(seed, dev, B=4, L=80, Nq=37, H=768):
 
 def _worker(rank, world, port, ret, shard):
     import torch.distributed as dist
+    os.environ["GOAT_PEER_EXCHANGE"] = "0" if shard == "nccl" else "1"
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
@@ -54,22 +55,26 @@ def _worker(rank, world, port, ret, shard):
         b = _batch(100 + rank, dev)
         active = engine.active_parameters(model, loss_fn, b)
         flat = engine.FlatParams(model, shadow_dtype=torch.bfloat16, only=active)
-        ts = engine.TrainStep(flat, loss_fn, b, use_graph=False, lr=1e-3, max_grad_norm=0.05, shard_optimizer=shard)
+        ts = engine.TrainStep(flat, loss_fn, b, use_graph=False, lr=1e-3, max_grad_norm=0.05, shard_optimizer=bool(shard))
         ts.step(b)
         ts.step(b)
+        if shard == "peer":       # the NVLink peer-memory exchange must be what ran, not the NCCL fallback
+            assert isinstance(flat._peer, dict), "peer-memory exchange was not set up"
         flat.sync_master()          # sharded steps leave the fp32 master weights current on their owner rank only
         torch.cuda.synchronize()
         ret.put((rank, flat.p[:flat.numel].detach().cpu().numpy(), flat.shadow[:flat.numel].float().cpu().numpy(),
                  flat.grad_norm.item()))     # numpy: pickled by value (tensors travel as handles that die with the worker)
         dist.barrier()
+        flat.release_peers()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("shard", [False, True])
+@pytest.mark.parametrize("shard", [False, "nccl", "peer"])
 def test_two_rank_step_matches_averaged_gradient_step(shard):
-    """shard=False: all-reduce + full AdamW on every rank; shard=True: reduce-scatter + AdamW on 1/world + all-gather."""
+    """shard=False: all-reduce + full AdamW on every rank; "nccl": reduce-scatter + AdamW on 1/world + all-gather;
+    "peer": the same step through csrc/exchange.cu (peer loads of the gradient shards, AdamW storing into every rank)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp

@@ -52,6 +52,9 @@ class AttnArgs(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/goat_sm100.h declares
+MAX_PEERS = 8              # GOAT_MAX_PEERS (include/goat_sm100.h)
+PEER_HANDLE_BYTES = 64     # GOAT_PEER_HANDLE_BYTES
+
 SYMBOLS = {
     "goat_version": (C.c_int, []),
     "goat_last_error": (C.c_char_p, []),
@@ -80,6 +83,18 @@ SYMBOLS = {
                                   C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "goat_scaler_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "goat_peer_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "goat_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "goat_peer_close": (C.c_int, [C.c_void_p]),
+    "goat_peer_signal_bytes": (C.c_size_t, []),
+    "goat_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "goat_peer_sum_scalar": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "goat_peer_reduce_sumsq": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_int), C.c_void_p]),
+    "goat_adamw_step_peers": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
+                                        C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "goat_act_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "goat_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "goat_act_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),

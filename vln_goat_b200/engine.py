@@ -117,6 +117,8 @@ class FlatParams(object):
                 runtime.register_split_buffer(buf, tot)
             self._shadow_buf = buf
         self._g_shard = self._x_shard = None
+        self._phase_events = None          # profile_phases(True): CUDA events around the phases of sharded_step
+        self._peer = None                  # None: not set up yet; False: NCCL collectives; dict: peer pointer tables
         self.master_synced = True
         self.scaler = None
         self._scaler_cfg = None
@@ -214,6 +216,28 @@ class FlatParams(object):
                           (1.0 - betas[1] ** t) if correct_bias else 1.0, max_grad_norm, grad_scale], dtype=torch.float32)
         self._hp.copy_(h, non_blocking=True)
 
+    def profile_phases(self, on=True):
+        """Record CUDA events around the phases of ``sharded_step`` (reduce-scatter, norm, AdamW, all-gather, fp32 tail);
+        ``phase_times()`` synchronises and returns the mean milliseconds per phase."""
+        self._phase_events = [] if on else None
+
+    def _phase(self, name):
+        if self._phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._phase_events.append((name, e))
+
+    def phase_times(self):
+        ev = self._phase_events or []
+        torch.cuda.synchronize()
+        tot, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+            if n1 == "begin":
+                continue
+            tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        return {k: tot[k] / cnt[k] for k in tot}
+
     def sharded_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=-1.0, correct_bias=True):
         """One data-parallel optimizer step with the optimizer state's work split over the ranks (see above).
         Afterwards every rank holds the new 16-bit operand shadow and the new fp32 no-decay vectors (biases,
@@ -230,8 +254,15 @@ class FlatParams(object):
         S, lo, n_decay_local = D.shard_layout(self.padded, self.n_decay, W, rank)
         if self._g_shard is None:
             self._g_shard = torch.zeros(S, device=self.p.device, dtype=torch.float32)
+        if self._peer is None:
+            self._peer_setup()
+        if self._peer:
+            return self._sharded_step_peers(S, lo, rank, lr, betas, eps, weight_decay, max_grad_norm, correct_bias)
+        if self._x_shard is None:
             self._x_shard = torch.zeros(S, device=self.p.device, dtype=self.shadow_dtype or torch.float32)
+        self._phase("begin")
         D.reduce_scatter_sum(self._g_shard, self.g, self.group)
+        self._phase("reduce_scatter")
         self.g.zero_()                      # the next step's gradients accumulate into a cleared buffer
         self._hp_upload(lr, betas, eps, weight_decay, max_grad_norm, 1.0 / W, correct_bias)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -241,6 +272,7 @@ class FlatParams(object):
         tot = self._partial[:nparts.value].sum().reshape(1)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)     # global squared norm of the summed gradient
         self._partial[:1].copy_(tot)
+        self._phase("zero_and_norm")
         sd = ops.dt(self.shadow_dtype) if self.shadow is not None else 0
         _lib.check(L.goat_adamw_step(self.p[lo:lo + S].data_ptr(), self._g_shard.data_ptr(), self.m[lo:lo + S].data_ptr(),
                                      self.v[lo:lo + S].data_ptr(),
@@ -251,20 +283,156 @@ class FlatParams(object):
                    "goat_adamw_step")
         ops.LAUNCHES[0] += 2
         self._scaler_update(1, st)
+        self._phase("adamw_shard")
         if self.shadow is not None:
             self._x_shard.copy_(self.shadow[lo:lo + S])
             D.all_gather_flat(self.shadow, self._x_shard, self.group)
             if self.shadow_lo is not None:
                 self._x_shard.copy_(self.shadow_lo[lo:lo + S])
                 D.all_gather_flat(self.shadow_lo, self._x_shard, self.group)
+            self._phase("all_gather_shadow")
             # everything the kernels read in FP32 (embedding tables, LayerNorm gains, pooling / gate vectors, biases):
             # each owner broadcasts its piece of [n_shadow_only, numel)
             for r, a, b in D.tail_pieces(self.n_shadow_only, self.numel, S, W):
                 dist.broadcast(self.p[a:b], src=D.group_src(r, self.group), group=self.group)
+            self._phase("broadcast_fp32_tail")
             self.master_synced = False
         else:
             self._x_shard.copy_(self.p[lo:lo + S])
             D.all_gather_flat(self.p, self._x_shard, self.group)
+        from . import runtime
+        runtime.bump_generation()
+
+    # ------------------------------------------------------------------------------------------
+    # the same step over NVLink peer memory (csrc/exchange.cu): every rank maps the other ranks' p / g / shadow buffers
+    # (CUDA IPC), reads its shard of everybody's gradients in the reduce kernel and stores the updated values straight
+    # into everybody's buffers from the AdamW kernel.  Two kernels + three scalar all-reduces (norm / barriers) replace
+    # reduce-scatter, staging copies, two all-gathers and the tail broadcasts.
+    # ------------------------------------------------------------------------------------------
+    def _peer_setup(self):
+        """Collective (first sharded step).  Falls back to the NCCL collectives -- on every rank -- when the exchange
+        is switched off (GOAT_PEER_EXCHANGE=0), the backend is not NCCL, the world exceeds GOAT_MAX_PEERS or a buffer
+        cannot be exported / mapped."""
+        import os
+        import sys
+        import torch.distributed as dist
+        L = _lib.lib()
+        W = self.world
+        rank = dist.get_rank(self.group)
+        sig = torch.zeros(L.goat_peer_signal_bytes() // 4, device=self.p.device, dtype=torch.float32)
+        torch.cuda.synchronize()             # the signal block is zero before any rank can learn its address
+        bufs = {"p": self.p, "g": self.g, "sig": sig}
+        if self.shadow is not None:
+            bufs["s"] = self._shadow_buf
+        mine, why = {}, None
+        if os.environ.get("GOAT_PEER_EXCHANGE", "1") == "0":
+            mine, why = None, "GOAT_PEER_EXCHANGE=0"
+        elif dist.get_backend(self.group) != "nccl" or W > _lib.MAX_PEERS:
+            mine, why = None, "backend %s, world %d" % (dist.get_backend(self.group), W)
+        else:
+            for k, t in bufs.items():
+                h = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+                off = C.c_ulonglong(0)
+                if L.goat_peer_export(C.c_void_p(t.data_ptr()), h, C.byref(off)) != 0:
+                    mine, why = None, L.goat_last_error().decode()
+                    break
+                mine[k] = (bytes(h), int(off.value))
+        every = [None] * W
+        dist.all_gather_object(every, mine, group=self.group)
+        ptrs, opened, ok = {k: [] for k in bufs}, {}, all(e is not None for e in every)
+        if ok:
+            for q in range(W):
+                for k, t in bufs.items():
+                    if q == rank:
+                        ptrs[k].append(t.data_ptr())
+                        continue
+                    hb, off = every[q][k]
+                    if hb not in opened:
+                        base = C.c_void_p(0)
+                        if L.goat_peer_open(hb, C.byref(base)) != 0:
+                            ok, why = False, L.goat_last_error().decode()
+                            break
+                        opened[hb] = base.value
+                    ptrs[k].append(opened[hb] + off)
+                if not ok:
+                    break
+        flags = [None] * W
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        if not all(flags):
+            for base in opened.values():
+                L.goat_peer_close(C.c_void_p(base))
+            if rank == 0 and os.environ.get("GOAT_PEER_EXCHANGE", "1") != "0":
+                sys.stderr.write("vln_goat_b200: peer-memory gradient exchange unavailable (%s); using NCCL collectives\n"
+                                 % (why or "another rank could not map the buffers"))
+            self._peer = False
+            return
+        arr = lambda xs: (C.c_void_p * W)(*xs)
+        esz = self.shadow.element_size() if self.shadow is not None else 0
+        self._peer = {"p": arr(ptrs["p"]), "g": arr(ptrs["g"]), "opened": opened, "sig": arr(ptrs["sig"]), "sig_t": sig,
+                      "epoch": 0, "side": torch.cuda.Stream(device=self.p.device),
+                      "nccl_sync": os.environ.get("GOAT_PEER_SYNC", "flags") == "nccl",
+                      "s": arr(ptrs["s"]) if self.shadow is not None else None,
+                      "slo": arr([b + self.padded * esz for b in ptrs["s"]]) if self.shadow_lo is not None else None}
+        self._sync = torch.zeros(1, device=self.p.device, dtype=torch.float32)
+
+    def release_peers(self):
+        """Unmap the other ranks' buffers (collective-free; call before the process group is destroyed)."""
+        if self._peer:
+            torch.cuda.synchronize()
+            for base in self._peer["opened"].values():
+                _lib.lib().goat_peer_close(C.c_void_p(base))
+        self._peer = None
+
+    def _peer_barrier(self, st, rank):
+        P = self._peer
+        if P["nccl_sync"]:
+            import torch.distributed as dist
+            dist.all_reduce(self._sync, group=self.group)
+            return
+        P["epoch"] += 1
+        _lib.check(_lib.lib().goat_peer_barrier(P["sig"], self.world, rank, P["epoch"] & 0xFFFFFFFF, st), "goat_peer_barrier")
+        ops.LAUNCHES[0] += 1
+
+    def _sharded_step_peers(self, S, lo, rank, lr, betas, eps, weight_decay, max_grad_norm, correct_bias):
+        L, P, W = _lib.lib(), self._peer, self.world
+        cur = torch.cuda.current_stream()
+        st = C.c_void_p(cur.cuda_stream)
+        self._hp_upload(lr, betas, eps, weight_decay, max_grad_norm, 1.0 / W, correct_bias)
+        self._phase("begin")
+        self._peer_barrier(st, rank)                 # every rank's backward is done: its gradients may be read
+        self._phase("barrier_backward_done")
+        nparts = C.c_int(0)
+        _lib.check(L.goat_peer_reduce_sumsq(P["g"], W, lo, S, self._g_shard.data_ptr(), self._partial.data_ptr(),
+                                            C.byref(nparts), st), "goat_peer_reduce_sumsq")
+        self._phase("peer_reduce_sumsq")
+        # global squared norm, the same bits on every rank; also the barrier "everybody has read my gradients"
+        if P["nccl_sync"]:
+            import torch.distributed as dist
+            tot = self._partial[:nparts.value].sum().reshape(1)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            self._partial[:1].copy_(tot)
+        else:
+            P["epoch"] += 1
+            _lib.check(L.goat_peer_sum_scalar(P["sig"], W, rank, P["epoch"] & 0xFFFFFFFF, self._partial.data_ptr(),
+                                              nparts.value, self._partial.data_ptr(), st), "goat_peer_sum_scalar")
+        self._phase("norm_exchange")
+        P["side"].wait_stream(cur)                   # clearing the gradient buffer (HBM) runs beside the AdamW kernel,
+        with torch.cuda.stream(P["side"]):           # whose time at larger worlds is the NVLink stores
+            self.g.zero_()
+        sd = ops.dt(self.shadow_dtype) if self.shadow is not None else 0
+        _lib.check(L.goat_adamw_step_peers(P["p"], P["s"], P["slo"], sd, W, rank, self._g_shard.data_ptr(),
+                                           self.m.data_ptr(), self.v.data_ptr(), lo, S, self.n_decay,
+                                           self.n_shadow_only if self.shadow is not None else 0, self._hp.data_ptr(),
+                                           self._partial.data_ptr(), 1, self.grad_norm.data_ptr(), _p_or_none(self.scaler), st),
+                   "goat_adamw_step_peers")
+        ops.LAUNCHES[0] += 3
+        self._scaler_update(1, st)
+        cur.wait_stream(P["side"])
+        self._phase("adamw_peers_and_zero")
+        self._peer_barrier(st, rank)                 # every rank's stores have landed before anybody's next forward
+        self._phase("barrier_stores_done")
+        if self.shadow is not None:
+            self.master_synced = False
         from . import runtime
         runtime.bump_generation()
 
