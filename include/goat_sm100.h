@@ -233,8 +233,9 @@ int goat_scaler_update(float* scaler, const float* partial, int nparts, float gr
  *               g_peers is a HOST array of `world` device pointers (own buffer included, at index rank).
  *               The caller must have synchronised the ranks (every rank's backward finished) before the launch.
  *   goat_adamw_step_peers: goat_adamw_step's arithmetic on the shard (g_shard indexed from 0; m, v and p indexed by flat
- *               element), and the new values are STORED TO EVERY RANK: shadow / shadow_lo (16-bit operand copies,
- *               optional) for every element, the fp32 value for elements >= n_fp32_from (0: all of them); the own
+ *               element), and the new values are STORED TO EVERY RANK, 4 bytes per element: shadow + shadow_lo (16-bit
+ *               operand copies, optional) for elements < n_fp32_from, the fp32 value for elements >= n_fp32_from (0: all
+ *               of them; their 16-bit copies are re-derived by each rank with goat_split_cast after the barrier); the own
  *               rank's fp32 master is always written.  A non-finite norm with a scaler changes nothing.  The caller
  *               synchronises the ranks again before anybody reads the buffers, and clears its own gradient buffer.
  *   goat_peer_barrier / goat_peer_sum_scalar: rank synchronisation through flags in peer memory (one 32-thread CTA, no
@@ -248,6 +249,8 @@ int goat_scaler_update(float* scaler, const float* partial, int nparts, float gr
  * ------------------------------------------------------------------------------------------ */
 #define GOAT_MAX_PEERS 8
 #define GOAT_PEER_HANDLE_BYTES 64
+/* hi = round(x) to F16/BF16, lo (optional) = round(x - hi): the split operand copies of an fp32 range (local). */
+int goat_split_cast(const float* x, void* hi, void* lo, int dtype, long long n, goat_stream_t stream);
 size_t goat_peer_signal_bytes(void);
 int goat_peer_barrier(void* const* signal_peers, int world, int rank, unsigned int epoch, goat_stream_t stream);
 int goat_peer_sum_scalar(void* const* signal_peers, int world, int rank, unsigned int epoch, const float* partial,

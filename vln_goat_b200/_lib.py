@@ -86,6 +86,7 @@ SYMBOLS = {
     "goat_peer_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "goat_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "goat_peer_close": (C.c_int, [C.c_void_p]),
+    "goat_split_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "goat_peer_signal_bytes": (C.c_size_t, []),
     "goat_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     "goat_peer_sum_scalar": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_int, C.c_void_p,

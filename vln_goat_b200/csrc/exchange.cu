@@ -190,8 +190,13 @@ adamw_peers_kernel(PeerPtrs pp, PeerPtrs sh, PeerPtrs shlo, int world, int rank,
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(pp.p[r]) + e0 + 4) = *reinterpret_cast<const float4*>(x + 4);
         }
         if constexpr (sizeof(TS) == 2) {
-          if (sh.p[r]) *reinterpret_cast<uint4*>(reinterpret_cast<TS*>(sh.p[r]) + e0) = hi;
-          if (shlo.p[r]) *reinterpret_cast<uint4*>(reinterpret_cast<TS*>(shlo.p[r]) + e0) = l4;
+          // 4 bytes per element and rank either way: the fp32 value (its 16-bit copies are re-derived locally by
+          // goat_split_cast) or hi + lo.  Storing all three for the fp32 region made its owners (the last ranks: embedding
+          // tables) send twice the bytes of the others -- 2.7 ms instead of 1.0 ms at 8 GPUs, everybody waiting for them.
+          if (!fp32_everywhere) {
+            if (sh.p[r]) *reinterpret_cast<uint4*>(reinterpret_cast<TS*>(sh.p[r]) + e0) = hi;
+            if (shlo.p[r]) *reinterpret_cast<uint4*>(reinterpret_cast<TS*>(shlo.p[r]) + e0) = l4;
+          }
         }
       }
     }
@@ -212,9 +217,11 @@ adamw_peers_kernel(PeerPtrs pp, PeerPtrs sh, PeerPtrs shlo, int world, int rank,
         if (r >= world) continue;
         if (e >= n_fp32_from) reinterpret_cast<float*>(pp.p[r])[e] = x;
         if constexpr (sizeof(TS) == 2) {
-          const TS h = from_f<TS>(x);
-          if (sh.p[r]) reinterpret_cast<TS*>(sh.p[r])[e] = h;
-          if (shlo.p[r]) reinterpret_cast<TS*>(shlo.p[r])[e] = from_f<TS>(x - to_f<TS>(h));
+          if (e < n_fp32_from) {
+            const TS h = from_f<TS>(x);
+            if (sh.p[r]) reinterpret_cast<TS*>(sh.p[r])[e] = h;
+            if (shlo.p[r]) reinterpret_cast<TS*>(shlo.p[r])[e] = from_f<TS>(x - to_f<TS>(h));
+          }
         }
       }
     }
@@ -262,6 +269,34 @@ peer_sum_scalar_kernel(PeerPtrs sig, int world, int rank, unsigned epoch, const 
     float tot = 0.f;
     for (int q = 0; q < world; ++q) tot += mine[slot + q];
     out[0] = tot;
+  }
+}
+
+// hi = round16(x), lo = round16(x - hi): the split operand copies of an fp32 range (local; HBM-bound, 8 B per element)
+template <typename TS>
+__global__ void __launch_bounds__(XCH_THREADS)
+split_cast_kernel(const float* __restrict__ x, TS* __restrict__ hi, TS* __restrict__ lo, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    uint2 h;
+    h.x = pack2<TS>(a.x, a.y);
+    h.y = pack2<TS>(a.z, a.w);
+    reinterpret_cast<uint2*>(hi)[i] = h;
+    if (lo) {
+      const float2 h0 = unpack2<TS>(h.x), h1 = unpack2<TS>(h.y);
+      uint2 l;
+      l.x = pack2<TS>(a.x - h0.x, a.y - h0.y);
+      l.y = pack2<TS>(a.z - h1.x, a.w - h1.y);
+      reinterpret_cast<uint2*>(lo)[i] = l;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const TS h = from_f<TS>(x[i]);
+      hi[i] = h;
+      if (lo) lo[i] = from_f<TS>(x[i] - to_f<TS>(h));
+    }
   }
 }
 
@@ -390,6 +425,21 @@ extern "C" int goat_peer_sum_scalar(void* const* signal_peers, int world, int ra
   PeerPtrs sig;
   fill_peers(sig, signal_peers, world);
   peer_sum_scalar_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sig, world, rank, epoch, partial, nparts, out);
+  GOAT_LAUNCH_CHECK();
+  return GOAT_OK;
+}
+
+extern "C" int goat_split_cast(const float* x, void* hi, void* lo, int dtype, long long n, goat_stream_t stream) {
+  GOAT_CHECK(x && hi, "goat_split_cast: null argument");
+  GOAT_CHECK(dtype == GOAT_F16 || dtype == GOAT_BF16, "goat_split_cast: dtype must be F16/BF16");
+  GOAT_CHECK(aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0,
+             "goat_split_cast: x must be 16-byte, hi / lo 8-byte aligned");
+  if (n <= 0) return GOAT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long want = (n / 4 + XCH_THREADS - 1) / XCH_THREADS;
+  const int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  if (dtype == GOAT_F16) split_cast_kernel<__half><<<grid, XCH_THREADS, 0, st>>>(x, (__half*)hi, (__half*)lo, n);
+  else split_cast_kernel<__nv_bfloat16><<<grid, XCH_THREADS, 0, st>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
   GOAT_LAUNCH_CHECK();
   return GOAT_OK;
 }

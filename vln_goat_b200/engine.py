@@ -170,9 +170,10 @@ class FlatParams(object):
         """Re-derive the 16-bit operand copies from the fp32 masters (after load_state_dict etc.)."""
         from . import runtime
         if self.shadow is not None:
-            ops.cast(self.p, self.shadow_dtype, out=self.shadow)
             if self.shadow_lo is not None:
-                self.shadow_lo.copy_(self.p - self.shadow.float())
+                ops.split_cast(self.p, self.shadow, self.shadow_lo)
+            else:
+                ops.cast(self.p, self.shadow_dtype, out=self.shadow)
         runtime.bump_generation()
 
     def begin_step(self):
@@ -431,6 +432,14 @@ class FlatParams(object):
         self._phase("adamw_peers_and_zero")
         self._peer_barrier(st, rank)                 # every rank's stores have landed before anybody's next forward
         self._phase("barrier_stores_done")
+        if self.shadow is not None and self.numel > self.n_shadow_only:
+            # the fp32-read region arrived as fp32 (4 B per element like hi + lo elsewhere): its operand copies are local work
+            a, n = self.n_shadow_only, self.numel - self.n_shadow_only
+            _lib.check(L.goat_split_cast(self.p[a:].data_ptr(), self.shadow[a:].data_ptr(),
+                                         self.shadow_lo[a:].data_ptr() if self.shadow_lo is not None else None, sd, n, st),
+                       "goat_split_cast")
+            ops.LAUNCHES[0] += 1
+            self._phase("split_cast_fp32_region")
         if self.shadow is not None:
             self.master_synced = False
         from . import runtime

@@ -277,6 +277,16 @@ def colsum(x, out=None, accumulate=False):
     return out
 
 
+def split_cast(x32, hi, lo):
+    """hi = x32 rounded to 16 bit, lo = (x32 - hi) rounded: the two terms of a split weight operand (goat_gemm B / B_lo)"""
+    if x32.dtype != torch.float32 or not x32.is_contiguous() or hi.dtype != lo.dtype or hi.numel() != x32.numel() \
+            or lo.numel() != x32.numel():
+        raise ValueError("split_cast: need a contiguous fp32 source and two 16-bit outputs of its size")
+    _lib.check(_lib.lib().goat_split_cast(_p(x32), _p(hi), _p(lo), dt(hi), x32.numel(), _stream()), "goat_split_cast")
+    LAUNCHES[0] += 1
+    return hi, lo
+
+
 def cast(src, dtype, out=None, drop_p=0.0, drop_seed=0, seed_ptr=None):
     """contiguous tensor -> new tensor (or `out`) of `dtype`; optional dropout mask by linear element index"""
     _req_cuda(src, out)

@@ -107,8 +107,7 @@ def _cast_split(p32, cdt):
     npad = (n + 7) // 8 * 8
     buf = torch.empty(2 * npad, device=p32.device, dtype=cdt)
     hi = buf[:n].view(p32.shape)
-    ops.cast(p32, cdt, out=buf[:n])
-    buf[npad:npad + n].copy_((p32.reshape(-1) - buf[:n].float()))
+    ops.split_cast(p32.reshape(-1), buf[:n], buf[npad:npad + n])
     register_split_buffer(buf, npad)
     return hi
 
