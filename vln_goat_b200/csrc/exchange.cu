@@ -141,67 +141,71 @@ adamw_peers_kernel(PeerPtrs pp, PeerPtrs sh, PeerPtrs shlo, int world, int rank,
   }
   const float step_size = lr * sqrtf(bc2) / bc1;
   float* p_own = reinterpret_cast<float*>(peer_at(pp, rank));
-  // 8 consecutive elements per thread: 16-byte loads of p, g, m, v and 16-byte peer stores of the 16-bit copies (a warp
-  // covers 512 contiguous bytes of hi and of lo per rank).  lo is a multiple of 8 (engine pads the shards).
-  const long long n8 = n >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const long long e0 = lo + i * 8;          // first flat element of this thread's eight
-    float x[8], gr8[8], mm[8], vv[8];
+  // A warp owns 256 consecutive elements and every lane two float4 columns of them (elements 4*lane.. and 128 + 4*lane..):
+  // each fp32 load / store instruction covers 512 contiguous bytes, each 16-bit store 256 -- whole 32-byte sectors, which
+  // is what peer stores need (16-byte stores at a 32-byte stride half-filled every sector and cost the owners of the fp32
+  // region 1.8 ms instead of 1.0 ms at 8 GPUs, profiles/r02p_peer_phases_n8_strided_stores.txt).
+  const long long nblk = n >> 8;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblk; blk += warps) {
+    float x[2][4], mm[2][4], vv[2][4];
+    float4 gg[2];
+    long long e[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      *reinterpret_cast<float4*>(x + 4 * h) = *reinterpret_cast<const float4*>(p_own + e0 + 4 * h);
-      *reinterpret_cast<float4*>(gr8 + 4 * h) = __ldcs(reinterpret_cast<const float4*>(g) + 2 * i + h);
-      *reinterpret_cast<float4*>(mm + 4 * h) = *reinterpret_cast<const float4*>(m + e0 + 4 * h);
-      *reinterpret_cast<float4*>(vv + 4 * h) = *reinterpret_cast<const float4*>(v + e0 + 4 * h);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gr = gr8[j] * coef;
-      mm[j] = mm[j] * b1 + gr * (1.f - b1);
-      vv[j] = vv[j] * b2 + gr * gr * (1.f - b2);
-      float y = x[j] - step_size * (mm[j] / (sqrtf(vv[j]) + eps));
-      if (e0 + j < n_decay) y -= y * (lr * wd);
-      x[j] = y;
+      const long long i = blk * 256 + h * 128 + lane * 4;     // index inside the shard
+      e[h] = lo + i;
+      *reinterpret_cast<float4*>(x[h]) = *reinterpret_cast<const float4*>(p_own + e[h]);
+      gg[h] = __ldcs(reinterpret_cast<const float4*>(g + i));
+      *reinterpret_cast<float4*>(mm[h]) = *reinterpret_cast<const float4*>(m + e[h]);
+      *reinterpret_cast<float4*>(vv[h]) = *reinterpret_cast<const float4*>(v + e[h]);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      *reinterpret_cast<float4*>(m + e0 + 4 * h) = *reinterpret_cast<const float4*>(mm + 4 * h);
-      *reinterpret_cast<float4*>(v + e0 + 4 * h) = *reinterpret_cast<const float4*>(vv + 4 * h);
-    }
-    const bool fp32_everywhere = e0 >= n_fp32_from;   // region boundaries are multiples of 8: never splits a thread's eight
-    if (!fp32_everywhere) {
-      *reinterpret_cast<float4*>(p_own + e0) = *reinterpret_cast<const float4*>(x);
-      *reinterpret_cast<float4*>(p_own + e0 + 4) = *reinterpret_cast<const float4*>(x + 4);
-    }
-    uint4 hi = make_uint4(0u, 0u, 0u, 0u), l4 = hi;
-    if constexpr (sizeof(TS) == 2) {
-      hi.x = pack2<TS>(x[0], x[1]); hi.y = pack2<TS>(x[2], x[3]); hi.z = pack2<TS>(x[4], x[5]); hi.w = pack2<TS>(x[6], x[7]);
-      const float2 h0 = unpack2<TS>(hi.x), h1 = unpack2<TS>(hi.y), h2 = unpack2<TS>(hi.z), h3 = unpack2<TS>(hi.w);
-      l4.x = pack2<TS>(x[0] - h0.x, x[1] - h0.y);
-      l4.y = pack2<TS>(x[2] - h1.x, x[3] - h1.y);
-      l4.z = pack2<TS>(x[4] - h2.x, x[5] - h2.y);
-      l4.w = pack2<TS>(x[6] - h3.x, x[7] - h3.y);
+      const float* ga = &gg[h].x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gr = ga[j] * coef;
+        mm[h][j] = mm[h][j] * b1 + gr * (1.f - b1);
+        vv[h][j] = vv[h][j] * b2 + gr * gr * (1.f - b2);
+        float y = x[h][j] - step_size * (mm[h][j] / (sqrtf(vv[h][j]) + eps));
+        if (e[h] + j < n_decay) y -= y * (lr * wd);
+        x[h][j] = y;
+      }
+      *reinterpret_cast<float4*>(m + e[h]) = *reinterpret_cast<const float4*>(mm[h]);
+      *reinterpret_cast<float4*>(v + e[h]) = *reinterpret_cast<const float4*>(vv[h]);
     }
 #pragma unroll
-    for (int r = 0; r < GOAT_MAX_PEERS; ++r) {
-      if (r < world) {
-        if (fp32_everywhere) {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(pp.p[r]) + e0) = *reinterpret_cast<const float4*>(x);
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(pp.p[r]) + e0 + 4) = *reinterpret_cast<const float4*>(x + 4);
-        }
-        if constexpr (sizeof(TS) == 2) {
+    for (int h = 0; h < 2; ++h) {
+      const float4 x4 = *reinterpret_cast<const float4*>(x[h]);
+      const bool fp32_everywhere = e[h] >= n_fp32_from;   // region boundaries are multiples of 8: never inside a float4
+      if (!fp32_everywhere) *reinterpret_cast<float4*>(p_own + e[h]) = x4;
+      uint2 hi = make_uint2(0u, 0u), l2 = hi;
+      if constexpr (sizeof(TS) == 2) {
+        hi.x = pack2<TS>(x4.x, x4.y);
+        hi.y = pack2<TS>(x4.z, x4.w);
+        const float2 h0 = unpack2<TS>(hi.x), h1 = unpack2<TS>(hi.y);
+        l2.x = pack2<TS>(x4.x - h0.x, x4.y - h0.y);
+        l2.y = pack2<TS>(x4.z - h1.x, x4.w - h1.y);
+      }
+#pragma unroll
+      for (int r = 0; r < GOAT_MAX_PEERS; ++r) {
+        if (r < world) {
           // 4 bytes per element and rank either way: the fp32 value (its 16-bit copies are re-derived locally by
           // goat_split_cast) or hi + lo.  Storing all three for the fp32 region made its owners (the last ranks: embedding
           // tables) send twice the bytes of the others -- 2.7 ms instead of 1.0 ms at 8 GPUs, everybody waiting for them.
-          if (!fp32_everywhere) {
-            if (sh.p[r]) *reinterpret_cast<uint4*>(reinterpret_cast<TS*>(sh.p[r]) + e0) = hi;
-            if (shlo.p[r]) *reinterpret_cast<uint4*>(reinterpret_cast<TS*>(shlo.p[r]) + e0) = l4;
+          if (fp32_everywhere) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(pp.p[r]) + e[h]) = x4;
+          } else if constexpr (sizeof(TS) == 2) {
+            if (sh.p[r]) *reinterpret_cast<uint2*>(reinterpret_cast<TS*>(sh.p[r]) + e[h]) = hi;
+            if (shlo.p[r]) *reinterpret_cast<uint2*>(reinterpret_cast<TS*>(shlo.p[r]) + e[h]) = l2;
           }
         }
       }
     }
   }
-  const long long n4 = n8 << 1;    // the scalar tail below starts at element n4 * 4 = n8 * 8
+  const long long n4 = nblk << 6;    // the scalar tail below starts at element n4 * 4 = nblk * 256
   if (blockIdx.x == 0) {
     for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       const long long e = lo + i;
