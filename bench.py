@@ -698,7 +698,7 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
     for r in rec:
         uniq[r] = uniq.get(r, 0) + 1
     dev = torch.device("cuda", torch.cuda.current_device())
-    umma_ms, umma_flop, n_umma, simt_ms = 0.0, 0.0, 0, 0.0
+    umma_ms, umma_flop, n_umma, simt_ms, exec_flop = 0.0, 0.0, 0, 0.0, 0.0
     table = []
     from vln_goat_b200 import runtime
     n_split = 0
@@ -733,6 +733,7 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
         else:
             umma_ms += ms * cnt
             umma_flop += 2.0 * M * N * K * cnt
+            exec_flop += 2.0 * M * N * K * cnt * (2 if has_lo else 1)
             n_umma += cnt
     achieved = umma_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
     round_ms = 3.0 * step_ms
@@ -757,8 +758,10 @@ def gemm_roofline(torch, ops, ts, resident, step_ms):
             "operand_bytes_per_round": algo_bytes,
             "peak_source": which, "flop_per_round": umma_flop, "gemm_ms_per_round": umma_ms, "simt_gemm_ms_per_round": simt_ms,
             "split_weight_launches": n_split,
+            "executed_tflops": exec_flop / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0,
+            "executed_frac": (exec_flop / (umma_ms * 1e-3) / 1e12 / peak) if umma_ms > 0 else 0.0,
             "split_weight_note": ("forward GEMMs run the K loop twice (16-bit weight hi + lo terms, ~22-bit weights) for parity; "
-                                  "achieved counts the ALGORITHMIC 2MNK once") if n_split else None,
+                                  "achieved / frac count the ALGORITHMIC 2MNK once; executed_* count what the tensor pipe actually ran") if n_split else None,
             "gemm_share_of_step": umma_ms / round_ms if round_ms else None,
             "step_tflops": umma_flop / (round_ms * 1e-3) / 1e12 if round_ms else None}
 
