@@ -64,6 +64,9 @@ def parse():
                     help="plain 16-bit weight operands in the forward GEMMs (faster, ~1.6x the forward error)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip parity / rooflines / baselines / C2 (profiling runs)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: fix the global batch (SURVEY C3: 256) and give each rank global/N samples; a step is "
+                         "then one optimizer step over the global batch and `value` counts those (default: 64 per GPU, weak)")
     ap.add_argument("--selfcheck", action="store_true", help="(default at N>1; kept for old command lines)")
     ap.add_argument("--no-selfcheck", action="store_true",
                     help="N>1: skip the check of bit-identical parameters / equal forward outputs across ranks after the "
@@ -379,7 +382,8 @@ def run_goat(args):
         time.sleep(0.3)
     launches[0] = 0
     ms = timed(step_resident, args.steps)
-    value = world * args.steps / (ms / 1e3)
+    units = 1 if args.global_batch else world        # strong scaling counts global-batch steps, weak counts per-rank batches
+    value = units * args.steps / (ms / 1e3)
     gpu_launches = launches[0]
 
     # ---- end to end: host batch dict -> index builders + padding -> pinned -> H2D on a copy stream -> step -> loss D2H
@@ -427,7 +431,7 @@ def run_goat(args):
         lv_ = losses[:state["n"]].clone()
         if not bool(torch.isfinite(lv_).all()):
             raise RuntimeError("non-finite loss in the timed run: %s" % lv_.tolist())
-        return world * steps / (ms_ / 1e3), ms_, state["h2d"], lv_
+        return (1 if args.global_batch else world) * steps / (ms_ / 1e3), ms_, state["h2d"], lv_
 
     e2e, ms_e2e, h2d_bytes, lv = run_e2e(host, args.steps)
 
@@ -453,9 +457,9 @@ def run_goat(args):
     # ---- sustained: the device-resident loop for >= 2 s
     sustained = None
     if not args.no_extras:
-        n_s = max(args.steps, int(2.2 * value / world) // 3 * 3 + 3)
+        n_s = max(args.steps, int(2.2 * value / units) // 3 * 3 + 3)
         ms_s = timed(step_resident, n_s)
-        sustained = {"steps": n_s, "seconds": ms_s / 1e3, "value": world * n_s / (ms_s / 1e3), "unit": "steps/s"}
+        sustained = {"steps": n_s, "seconds": ms_s / 1e3, "value": units * n_s / (ms_s / 1e3), "unit": "steps/s"}
     clk = clocks.stop() if rank == 0 else None
 
     if os.environ.get("GOAT_SHARD_TIMING") and world > 1:      # diagnostic, outside every timed region
@@ -478,7 +482,8 @@ def run_goat(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak", "samples_per_s": B * world * args.steps / (ms / 1e3),
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
                        "dropout": 0.1, "cuda_graph": not args.no_graph, "captured_graphs": n_graphs,
@@ -956,7 +961,14 @@ def run_c4(torch, cdt, dev, episodes=16, T=15, reps=4):
 
 
 def main():
+    global B, WORKLOAD
     args = parse()
+    if args.global_batch:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of ranks")
+        B = args.global_batch // world
+        WORKLOAD = WORKLOAD.replace("batch 64 per GPU", "GLOBAL batch %d = %d per GPU (strong scaling)" % (args.global_batch, B))
     if args.impl == "reference":
         run_reference(args)
     else:
