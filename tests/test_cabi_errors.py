@@ -71,3 +71,52 @@ def test_layernorm_and_colsum_validation():
     rc = L.goat_colsum_acc(0x1000, _lib.BF16, 16, 12, 12, 0x1000, None)     # 12 is not a multiple of 8 columns
     assert rc == INVALID and "multiples" in _err()
     assert L.goat_colsum_acc(0x1000, _lib.BF16, 0, 16, 16, 0x1000, None) == 0   # no rows: success, no launch
+
+
+def _ptrs(vals):
+    return (C.c_void_p * len(vals))(*vals)
+
+
+def test_peer_exchange_validation():
+    """csrc/exchange.cu: world / rank / alignment / null checks happen on the host before any launch."""
+    L = _lib.lib()
+    assert L.goat_peer_signal_bytes() >= 4 * (_lib.MAX_PEERS + 2 * _lib.MAX_PEERS)
+    n = C.c_int(0)
+    two = _ptrs([0x1000, 0x2000])
+    # reduce: world outside 1..GOAT_MAX_PEERS, unaligned shard start, null peer pointer
+    assert L.goat_peer_reduce_sumsq(two, _lib.MAX_PEERS + 1, 0, 64, 0x1000, 0x1000, C.byref(n), None) == INVALID
+    assert "world" in _err()
+    assert L.goat_peer_reduce_sumsq(two, 2, 2, 64, 0x1000, 0x1000, C.byref(n), None) == INVALID
+    assert "aligned" in _err()
+    assert L.goat_peer_reduce_sumsq(_ptrs([0x1000, None]), 2, 0, 64, 0x1000, 0x1000, C.byref(n), None) == INVALID
+    assert "bad peer pointer 1" in _err()
+    assert L.goat_peer_reduce_sumsq(None, 2, 0, 64, 0x1000, 0x1000, C.byref(n), None) == INVALID
+    # AdamW over peers: rank outside the world, shard start not a multiple of 8, shadow_lo without shadow, bad dtype
+    args = dict(p=two, s=two, slo=two, dt=_lib.F16, world=2, rank=0, lo=0, n=64, n_decay=64, n_fp32=0, nparts=1)
+
+    def adamw(**kw):
+        a = dict(args, **kw)
+        return L.goat_adamw_step_peers(a["p"], a["s"], a["slo"], a["dt"], a["world"], a["rank"], 0x1000, 0x1000, 0x1000,
+                                       a["lo"], a["n"], a["n_decay"], a["n_fp32"], 0x1000, 0x1000, a["nparts"], None, None,
+                                       None)
+    assert adamw(rank=2) == INVALID and "world / rank" in _err()
+    assert adamw(lo=4) == INVALID and "multiples of 8" in _err()
+    assert adamw(s=None) == INVALID and "shadow_lo needs shadow" in _err()
+    assert adamw(dt=_lib.F32) == INVALID and "shadow dtype" in _err()
+    assert adamw(nparts=0) == INVALID and "nparts" in _err()
+    assert adamw(p=_ptrs([0x1000, 0x1004])) == INVALID and "parameter pointer of rank 1" in _err()
+    assert adamw(n=0) == 0                                   # empty shard: nothing to do
+    # flag barrier / scalar exchange
+    assert L.goat_peer_barrier(None, 2, 0, 1, None) == INVALID
+    assert L.goat_peer_barrier(two, 2, 5, 1, None) == INVALID and "world / rank" in _err()
+    assert L.goat_peer_sum_scalar(two, 2, 0, 1, None, 1, 0x1000, None) == INVALID
+    assert L.goat_peer_sum_scalar(two, 2, 0, 1, 0x1000, 0, 0x1000, None) == INVALID and "nparts" in _err()
+    # split cast and handle export
+    assert L.goat_split_cast(0x1000, 0x1000, None, _lib.F32, 8, None) == INVALID and "dtype" in _err()
+    assert L.goat_split_cast(0x1004, 0x1000, None, _lib.F16, 8, None) == INVALID and "aligned" in _err()
+    assert L.goat_split_cast(None, 0x1000, None, _lib.F16, 8, None) == INVALID
+    assert L.goat_split_cast(0x1000, 0x1000, None, _lib.F16, 0, None) == 0
+    off = C.c_ulonglong(0)
+    assert L.goat_peer_export(None, (C.c_ubyte * _lib.PEER_HANDLE_BYTES)(), C.byref(off)) == INVALID
+    assert L.goat_peer_open(None, C.byref(C.c_void_p(0))) == INVALID
+    assert L.goat_peer_close(None) == 0
