@@ -41,3 +41,13 @@ def test_gpu_arm_fails_loudly_without_cuda():
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_global_batch_must_split_evenly_over_the_ranks():
+    """--global-batch N (strong scaling, SURVEY C3: 256) gives every rank N / world samples; an uneven split is refused
+    before anything touches a device."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="3", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "3", "--global-batch", "256"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode != 0
+    assert "multiple of the number of ranks" in (out.stderr + out.stdout)
